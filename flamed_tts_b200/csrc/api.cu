@@ -1,0 +1,872 @@
+// C ABI of libflamed_b200.so (see include/flamed_b200.h): context, weight packing and the host
+// orchestration of the four hot-path modules.  All compute is in the CUDA kernels of this
+// directory; there is no CPU fallback.
+#include <cuda.h>
+
+#include "engine.h"
+
+using namespace flm;
+
+static thread_local std::string g_last_error;
+
+#define FLM_API_BEGIN try {
+#define FLM_API_END                          \
+  return FLM_OK;                             \
+  }                                          \
+  catch (const flm::Error& e) {              \
+    g_last_error = e.what();                 \
+    return e.code;                           \
+  }                                          \
+  catch (const std::exception& e) {          \
+    g_last_error = e.what();                 \
+    return FLM_ERR_CUDA;                     \
+  }
+
+extern "C" const char* flm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int flm_version(void) { return 100; }
+
+// ===================================================================================== context
+extern "C" int flm_ctx_create(int device, flm_ctx** out) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(out != nullptr, "out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error(FLM_ERR_CUDA, "no CUDA device: flamed_b200 has no CPU fallback (needs an sm_100 GPU)");
+  FLM_REQUIRE(device >= 0 && device < count, "bad device index");
+  FLM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FLM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    throw Error(FLM_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                  ", the kernels are built for sm_100a only");
+  std::unique_ptr<flm_ctx> c(new flm_ctx);
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult qres;
+  FLM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &c->tma_encode, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !c->tma_encode)
+    throw Error(FLM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  tapgemm_tc_init();
+  *out = c.release();
+  FLM_API_END
+}
+extern "C" void flm_ctx_destroy(flm_ctx* ctx) { delete ctx; }
+
+static inline cudaStream_t S(flm_stream s) { return static_cast<cudaStream_t>(s); }
+static void set_device(flm_ctx* ctx) { FLM_CUDA(cudaSetDevice(ctx->device)); }
+
+static std::vector<float> replicate(const std::vector<float>& v, int times) {
+  std::vector<float> o;
+  o.reserve(v.size() * times);
+  for (int i = 0; i < times; ++i) o.insert(o.end(), v.begin(), v.end());
+  return o;
+}
+
+// ===================================================================================== durgen
+namespace {
+struct DurNet {
+  Layer encproj, te1, te3, c1, c2;
+  float *w0, *ln1w, *ln1b, *ln2w, *ln2b, *wl, *bl;
+  int D, F;
+  // per-call buffers
+  DevBuf encp, semb, teh, temb, a0, r1, l1, r2, xt;
+};
+}  // namespace
+
+struct flm_durgen : Engine {
+  DurNet net[2];
+  DevBuf enc_s, noise_s[2], mask_s, ts_s, out_s[2];
+  GraphCache graphs;
+  flm_durgen(flm_ctx* c) : Engine(c, FLM_F32) {}
+
+  void load_net(const WeightMap& wm, const std::string& p, DurNet& n) {
+    const flm_tensor& pw = wm.get(p + ".proj.weight");
+    const int D = (int)pw.shape[0];
+    FLM_REQUIRE(pw.ndim == 2 && pw.shape[1] == D + 1, "proj.weight must be (D, D+1)");
+    std::vector<float> w = wm.vec(p + ".proj.weight", {D, D + 1});
+    std::vector<float> w0(D), wenc((size_t)D * D);
+    for (int c = 0; c < D; ++c) {
+      w0[c] = w[(size_t)c * (D + 1)];
+      for (int k = 0; k < D; ++k) wenc[(size_t)c * D + k] = w[(size_t)c * (D + 1) + 1 + k];
+    }
+    n.D = D;
+    n.w0 = store.upload(w0);
+    n.encproj = make_layer(wenc, wm.vec(p + ".proj.bias", {D}), D, D, 1, 0, 1, 1, false);
+    const int TS = (int)wm.get(p + ".time_emb.time_emb.1.weight").shape[0];
+    n.te1 = make_layer(wm.vec(p + ".time_emb.time_emb.1.weight", {TS, D}), wm.vec(p + ".time_emb.time_emb.1.bias", {TS}),
+                       D, TS, 1, 0, 1, 1, false);
+    n.te3 = make_layer(wm.vec(p + ".time_emb.time_emb.3.weight", {D, TS}), wm.vec(p + ".time_emb.time_emb.3.bias", {D}),
+                       TS, D, 1, 0, 1, 1, false);
+    const flm_tensor& cw = wm.get(p + ".conv_layer.conv1d_1.conv.weight");
+    const int F = (int)cw.shape[0], k = (int)cw.shape[2];
+    FLM_REQUIRE(k == 3, "duration generator kernel_size must be 3");
+    n.F = F;
+    n.c1 = make_layer(pack_conv(wm.vec(p + ".conv_layer.conv1d_1.conv.weight", {F, D, k}), F, D, k),
+                      wm.vec(p + ".conv_layer.conv1d_1.conv.bias", {F}), D, F, k, -(k - 1) / 2, 1, 1, false);
+    n.c2 = make_layer(pack_conv(wm.vec(p + ".conv_layer.conv1d_2.conv.weight", {F, F, k}), F, F, k),
+                      wm.vec(p + ".conv_layer.conv1d_2.conv.bias", {F}), F, F, k, -1, 1, 1, false);
+    n.ln1w = store.upload(wm.vec(p + ".conv_layer.layer_norm_1.weight", {F}));
+    n.ln1b = store.upload(wm.vec(p + ".conv_layer.layer_norm_1.bias", {F}));
+    n.ln2w = store.upload(wm.vec(p + ".conv_layer.layer_norm_2.weight", {F}));
+    n.ln2b = store.upload(wm.vec(p + ".conv_layer.layer_norm_2.bias", {F}));
+    n.wl = store.upload(wm.vec(p + ".linear_layer.weight", {1, F}));
+    n.bl = store.upload(wm.vec(p + ".linear_layer.bias", {1}));
+  }
+
+  void body(int B, int P, int nfe, float temperature, cudaStream_t s) {
+    const int64_t rows = (int64_t)B * P;
+    const float dt = (float)(1.0 / nfe);
+    for (int g = 0; g < 2; ++g) {
+      DurNet& n = net[g];
+      launch_scale(noise_s[g].as<float>(), temperature, rows, n.xt.as<float>(), s);
+      gemm(problem(n.encproj, enc_s.p, n.D, B, P, P, n.encp.p, n.D, 0, EPI_NONE), n.encproj, false, s);
+      launch_sinusoidal_pos_emb(ts_s.as<float>(), nfe, n.D, n.semb.as<float>(), s);
+      gemm(problem(n.te1, n.semb.p, n.D, 1, nfe, nfe, n.teh.p, n.te1.N, 0, EPI_SILU), n.te1, false, s);
+      gemm(problem(n.te3, n.teh.p, n.te1.N, 1, nfe, nfe, n.temb.p, n.D, 0, EPI_NONE), n.te3, false, s);
+    }
+    for (int i = 0; i < nfe; ++i) {
+      for (int g = 0; g < 2; ++g) {
+        DurNet& n = net[g];
+        launch_durgen_input(n.encp.as<float>(), n.xt.as<float>(), n.w0, n.temb.as<float>() + (int64_t)i * n.D, rows,
+                            n.D, n.a0.as<float>(), s);
+        gemm(problem(n.c1, n.a0.p, n.D, B, P, P, n.r1.p, n.F, 0, EPI_NONE), n.c1, false, s);
+        LnMod ln;
+        memset(&ln, 0, sizeof(ln));
+        ln.x = n.r1.as<float>(); ln.ldx = n.F; ln.y = n.l1.p; ln.ldy = n.F; ln.y_bf16 = 0;
+        ln.w = n.ln1w; ln.b = n.ln1b; ln.eps = 1e-5f; ln.rows = rows; ln.rows_per_batch = P; ln.C = n.F;
+        ln.relu_in = 1;
+        launch_ln_mod(ln, s);
+        gemm(problem(n.c2, n.l1.p, n.F, B, P, P, n.r2.p, n.F, 0, EPI_NONE), n.c2, false, s);
+        launch_durgen_head(n.r2.as<float>(), rows, n.F, n.ln2w, n.ln2b, n.wl, n.bl, mask_s.as<uint8_t>(), dt,
+                           n.xt.as<float>(), s);
+      }
+    }
+    for (int g = 0; g < 2; ++g) launch_duration_round(net[g].xt.as<float>(), rows, out_s[g].as<float>(), s);
+  }
+};
+
+extern "C" int flm_durgen_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_durgen** out) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && weights && out, "null argument");
+  set_device(ctx);
+  WeightMap wm(weights, n);
+  std::unique_ptr<flm_durgen> h(new flm_durgen(ctx));
+  h->load_net(wm, "duration_generator", h->net[0]);
+  h->load_net(wm, "sil_generator", h->net[1]);
+  *out = h.release();
+  FLM_API_END
+}
+extern "C" void flm_durgen_destroy(flm_durgen* h) { delete h; }
+
+extern "C" int flm_durgen_sample(flm_durgen* h, const float* enc, const float* noise_dur, const float* noise_sil,
+                                 const uint8_t* src_mask, const float* ts_host, int nfe, float temperature, int B, int P,
+                                 float* out_phone, float* out_sil, float* out_dur_t, float* out_sil_t,
+                                 flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && enc && noise_dur && noise_sil && src_mask && ts_host && out_phone && out_sil, "null argument");
+  FLM_REQUIRE(nfe >= 1 && B >= 0 && P >= 1, "bad sizes");
+  set_device(h->ctx);
+  if (B == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int64_t rows = (int64_t)B * P;
+  bool moved = false;
+  moved |= h->enc_s.ensure(rows * h->net[0].D * 4);
+  moved |= h->mask_s.ensure(rows);
+  moved |= h->ts_s.ensure((nfe + 1) * 4);
+  for (int g = 0; g < 2; ++g) {
+    DurNet& n = h->net[g];
+    moved |= h->noise_s[g].ensure(rows * 4);
+    moved |= h->out_s[g].ensure(rows * 4);
+    moved |= n.encp.ensure(rows * n.D * 4);
+    moved |= n.semb.ensure((size_t)nfe * n.D * 4);
+    moved |= n.teh.ensure((size_t)nfe * n.te1.N * 4);
+    moved |= n.temb.ensure((size_t)nfe * n.D * 4);
+    moved |= n.a0.ensure(rows * n.D * 4);
+    moved |= n.r1.ensure(rows * n.F * 4);
+    moved |= n.l1.ensure(rows * n.F * 4);
+    moved |= n.r2.ensure(rows * n.F * 4);
+    moved |= n.xt.ensure(rows * 4);
+  }
+  if (moved) h->graphs.clear();
+  FLM_CUDA(cudaMemcpyAsync(h->enc_s.p, enc, rows * h->net[0].D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->noise_s[0].p, noise_dur, rows * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->noise_s[1].p, noise_sil, rows * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->mask_s.p, src_mask, rows, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts_host, (nfe + 1) * 4, cudaMemcpyHostToDevice, s));
+  int tbits;
+  memcpy(&tbits, &temperature, 4);
+  h->graphs.run(std::make_tuple(B, P, nfe, tbits), s,
+                [&](cudaStream_t cs) { h->body(B, P, nfe, temperature, cs); });
+  FLM_CUDA(cudaMemcpyAsync(out_phone, h->out_s[0].p, rows * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(out_sil, h->out_s[1].p, rows * 4, cudaMemcpyDeviceToDevice, s));
+  if (out_dur_t) FLM_CUDA(cudaMemcpyAsync(out_dur_t, h->net[0].xt.p, rows * 4, cudaMemcpyDeviceToDevice, s));
+  if (out_sil_t) FLM_CUDA(cudaMemcpyAsync(out_sil_t, h->net[1].xt.p, rows * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_API_END
+}
+
+// ===================================================================================== length regulator
+extern "C" int flm_lr_plan(flm_ctx* ctx, const float* phone_dur, const float* sil_dur, const int64_t* src_lens, int B,
+                           int P, int32_t* out_cumsum, int64_t* out_tgt_len, int64_t* out_tmax_host, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && phone_dur && sil_dur && src_lens && out_cumsum && out_tgt_len && out_tmax_host, "null argument");
+  set_device(ctx);
+  *out_tmax_host = 0;
+  if (B == 0) return FLM_OK;
+  launch_lr_plan(phone_dur, sil_dur, src_lens, B, P, out_cumsum, out_tgt_len, S(stream));
+  std::vector<int64_t> tl(B);
+  FLM_CUDA(cudaMemcpyAsync(tl.data(), out_tgt_len, (size_t)B * 8, cudaMemcpyDeviceToHost, S(stream)));
+  FLM_CUDA(cudaStreamSynchronize(S(stream)));  // the one documented sync (reference: pva.py:158 .tolist())
+  int64_t mx = 0;
+  for (int64_t v : tl) mx = std::max(mx, v);
+  *out_tmax_host = mx;
+  FLM_API_END
+}
+
+extern "C" int flm_lr_expand(flm_ctx* ctx, const float* x, const int32_t* cumsum, int B, int P, int H, int Tmax,
+                             float* out, int32_t* out_index, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && x && cumsum && out, "null argument");
+  set_device(ctx);
+  launch_lr_expand(x, cumsum, B, P, H, Tmax, out, out_index, S(stream));
+  FLM_API_END
+}
+
+// ===================================================================================== denoiser
+namespace {
+struct ConvNeXtW {
+  float *dw_w, *dw_b, *gn_w, *gn_b;
+  Layer conv2, conv3;
+};
+struct ResBlockW {
+  float *lnc_w, *lnc_b, *lnm_w, *lnm_b;
+  ConvNeXtW cn;
+  Layer mlp0, mlp2;
+};
+}  // namespace
+
+struct flm_denoiser : Engine {
+  flm_prob_cfg cfg;
+  int H, D, ada_n;
+  // denoiser weights
+  Layer time0, time2, cond_embed, proj_in, ada_all, conv_out;
+  std::vector<ResBlockW> blocks;
+  ConvNeXtW fin;
+  // cond down-sampler weights
+  float* qemb;
+  struct Stage { Layer conv_a, conv_b; float *gna_w, *gna_b, *gnb_w, *gnb_b; };
+  std::vector<Stage> stages;
+  Layer proj_out;
+  // buffers
+  DevBuf cond_s, spk_s, noise_s, ts_s, x, xb, h, bufU, bufD, bufG, bufA, part, gsc, gof, ada, sbuf, temb, tfreq, teh,
+      cvec, vout;
+  DevBuf c_prior, c_mask, c_xq, c_xm, c_h, c_part, c_sc, c_of, c_out;
+  GraphCache graphs;
+  flm_denoiser(flm_ctx* c, int mode) : Engine(c, mode) {}
+
+  ConvNeXtW load_convnext(const WeightMap& wm, const std::string& p) {
+    ConvNeXtW c;
+    const int k = cfg.kernel_size;
+    std::vector<float> w = wm.vec(p + ".conv_1.weight", {H, 1, k});
+    std::vector<float> wt((size_t)k * H);
+    for (int ch = 0; ch < H; ++ch)
+      for (int t = 0; t < k; ++t) wt[(size_t)t * H + ch] = w[(size_t)ch * k + t];
+    c.dw_w = store.upload(wt);
+    c.dw_b = store.upload(wm.vec(p + ".conv_1.bias", {H}));
+    c.gn_w = store.upload(wm.vec(p + ".ln_1.weight", {H}));
+    c.gn_b = store.upload(wm.vec(p + ".ln_1.bias", {H}));
+    c.conv2 = make_layer(wm.vec(p + ".conv_2.weight", {H, H, 1}), wm.vec(p + ".conv_2.bias", {H}), H, H, 1, 0, 1, 1, bf());
+    c.conv3 = make_layer(wm.vec(p + ".conv_3.weight", {H, H, 1}), wm.vec(p + ".conv_3.bias", {H}), H, H, 1, 0, 1, 1, bf());
+    return c;
+  }
+
+  void load(const WeightMap& wm) {
+    H = cfg.hidden_dim; D = cfg.target_dim;
+    const std::string dn = "denoiser";
+    time0 = make_layer(wm.vec(dn + ".time_embed.mlp.0.weight", {H, 256}), wm.vec(dn + ".time_embed.mlp.0.bias", {H}), 256, H, 1, 0, 1, 1, false);
+    time2 = make_layer(wm.vec(dn + ".time_embed.mlp.2.weight", {H, H}), wm.vec(dn + ".time_embed.mlp.2.bias", {H}), H, H, 1, 0, 1, 1, false);
+    cond_embed = make_layer(wm.vec(dn + ".cond_embed.weight", {H, cfg.spk_dim}), wm.vec(dn + ".cond_embed.bias", {H}), cfg.spk_dim, H, 1, 0, 1, 1, false);
+    proj_in = make_layer(wm.vec(dn + ".proj_in.weight", {H, D}), wm.vec(dn + ".proj_in.bias", {H}), D, H, 1, 0, 1, 1, bf());
+    std::vector<float> ada_w, ada_b;
+    for (int i = 0; i < cfg.n_layers; ++i) {
+      const std::string p = dn + ".res_blocks." + std::to_string(i);
+      ResBlockW b;
+      b.lnc_w = store.upload(wm.vec(p + ".ln_conv.weight", {H}));
+      b.lnc_b = store.upload(wm.vec(p + ".ln_conv.bias", {H}));
+      b.lnm_w = store.upload(wm.vec(p + ".ln_mlp.weight", {H}));
+      b.lnm_b = store.upload(wm.vec(p + ".ln_mlp.bias", {H}));
+      b.cn = load_convnext(wm, p + ".conv_in");
+      b.mlp0 = make_layer(wm.vec(p + ".mlp.0.weight", {H, H}), wm.vec(p + ".mlp.0.bias", {H}), H, H, 1, 0, 1, 1, bf());
+      b.mlp2 = make_layer(wm.vec(p + ".mlp.2.weight", {H, H}), wm.vec(p + ".mlp.2.bias", {H}), H, H, 1, 0, 1, 1, bf());
+      blocks.push_back(b);
+      std::vector<float> w = wm.vec(p + ".adaLN_modulation.1.weight", {6 * H, H});
+      std::vector<float> bb = wm.vec(p + ".adaLN_modulation.1.bias", {6 * H});
+      ada_w.insert(ada_w.end(), w.begin(), w.end());
+      ada_b.insert(ada_b.end(), bb.begin(), bb.end());
+    }
+    {
+      const std::string p = dn + ".final_layer";
+      std::vector<float> w = wm.vec(p + ".adaLN_modulation.1.weight", {5 * H, H});
+      std::vector<float> bb = wm.vec(p + ".adaLN_modulation.1.bias", {5 * H});
+      ada_w.insert(ada_w.end(), w.begin(), w.end());
+      ada_b.insert(ada_b.end(), bb.begin(), bb.end());
+      fin = load_convnext(wm, p + ".conv_in");
+      conv_out = make_layer(pack_conv(wm.vec(p + ".conv_out.weight", {D, H, 3}), D, H, 3), wm.vec(p + ".conv_out.bias", {D}),
+                            H, D, 3, -1, 1, 1, bf());
+    }
+    ada_n = (int)ada_b.size();  // 4*6H + 5H
+    // one projection for every adaLN of every block: rows = (step, sample)
+    ada_all = make_layer(ada_w, ada_b, H, ada_n, 1, 0, 1, 1, bf());
+    // cond down-sampler
+    const int Q = cfg.n_quantizers, CD = cfg.cond_dim;
+    qemb = store.upload(wm.vec("quantizer_encoding.quantizer_emb.weight", {Q, CD}));
+    int cin = Q * CD;
+    for (int s = 0; s < cfg.downsampling_stages; ++s) {
+      Stage st;
+      const std::string rp = "cond_downsampling.resblocks." + std::to_string(s) + ".block.block";
+      const std::string dp = "cond_downsampling.downblocks." + std::to_string(s);
+      st.conv_a = make_layer(wm.vec(rp + ".0.weight", {cin, cin, 1}), wm.vec(rp + ".0.bias", {cin}), cin, cin, 1, 0, 1, 1, bf());
+      st.gna_w = store.upload(wm.vec(rp + ".1.weight", {cin}));
+      st.gna_b = store.upload(wm.vec(rp + ".1.bias", {cin}));
+      st.conv_b = make_layer(wm.vec(dp + ".0.weight", {cin / 2, cin, 1}), wm.vec(dp + ".0.bias", {cin / 2}), cin, cin / 2, 1, 0, 1, 1, bf());
+      st.gnb_w = store.upload(wm.vec(dp + ".1.weight", {cin / 2}));
+      st.gnb_b = store.upload(wm.vec(dp + ".1.bias", {cin / 2}));
+      stages.push_back(st);
+      cin /= 2;
+    }
+    proj_out = make_layer(wm.vec("cond_downsampling.proj_out.0.weight", {D, cin}), wm.vec("cond_downsampling.proj_out.0.bias", {D}), cin, D, 1, 0, 1, 1, bf());
+  }
+
+  // ---- one ConvNeXt: hres += gate * (u + conv3(gelu(conv2(GN(dwconv(u))))))   (prob_generator.py:107-111,162)
+  void convnext(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s) {
+    const int b16 = bf() ? 1 : 0;
+    DwConv dw;
+    dw.x = bufU.p; dw.y = bufD.p; dw.io_bf16 = b16; dw.w = c.dw_w; dw.bias = c.dw_b; dw.part = part.as<float>();
+    dw.B = B; dw.L = L; dw.C = H; dw.KW = cfg.kernel_size;
+    launch_dwconv(dw, s);
+    launch_gn_finalize(part.as<float>(), B, L, H, H, dw_nchunk(L), DW_TT, c.gn_w, c.gn_b, 1e-5f, gsc.as<float>(),
+                       gof.as<float>(), s);
+    GnApply ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.x = bufD.p; ga.x_bf16 = b16; ga.y = bufG.p; ga.y_bf16 = b16; ga.scale = gsc.as<float>();
+    ga.offset = gof.as<float>(); ga.B = B; ga.L = L; ga.C = H;
+    launch_gn_apply(ga, s);
+    gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
+    TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
+    p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
+    p.hres = h.as<float>(); p.ld_res = H;
+    gemm(p, c.conv3, bf(), s);
+  }
+
+  void ln_modulate(const float* w, const float* b, const float* shift, const float* scale, int B, int L, void* y,
+                   cudaStream_t s) {
+    LnMod ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = h.as<float>(); ln.ldx = H; ln.y = y; ln.ldy = H; ln.y_bf16 = bf() ? 1 : 0;
+    ln.w = w; ln.b = b; ln.shift = shift; ln.scale = scale; ln.mod_bstride = ada_n; ln.scale_plus_one = 1.f;
+    ln.eps = 1e-6f; ln.rows = (int64_t)B * L; ln.rows_per_batch = L; ln.C = H;
+    launch_ln_mod(ln, s);
+  }
+
+  // adaLN table for `nfe` time points: ada[(i*B+b), :]   (hoisted out of the loop)
+  void modulation_table(int B, int nfe, cudaStream_t s) {
+    launch_timestep_embedding(ts_s.as<float>(), nfe, 256, tfreq.as<float>(), s);
+    gemm(problem(time0, tfreq.p, 256, 1, nfe, nfe, teh.p, H, 0, EPI_SILU), time0, false, s);
+    gemm(problem(time2, teh.p, H, 1, nfe, nfe, temb.p, H, 0, EPI_NONE), time2, false, s);
+    gemm(problem(cond_embed, spk_s.p, cfg.spk_dim, 1, B, B, cvec.p, H, 0, EPI_NONE), cond_embed, false, s);
+    launch_silu_sum(temb.as<float>(), cvec.as<float>(), nfe, B, H, sbuf.p, bf() ? 1 : 0, s);
+    gemm(problem(ada_all, sbuf.p, H, 1, nfe * B, nfe * B, ada.p, ada_n, 0, EPI_NONE), ada_all, bf(), s);
+  }
+
+  // one velocity evaluation at table row `i`, accumulated as target += alpha * v
+  void step(int B, int L, int i, float* target, float alpha, cudaStream_t s) {
+    const int64_t M = (int64_t)B * L;
+    const float* xin = x.as<float>();
+    if (bf()) {
+      launch_f32_to_bf16(xin, xb.as<bf16>(), M * D, s);
+      gemm(problem(proj_in, xb.p, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, true, s);
+    } else {
+      gemm(problem(proj_in, xin, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, false, s);
+    }
+    const float* arow = ada.as<float>() + (int64_t)i * B * ada_n;
+    const int b16 = bf() ? 1 : 0;
+    for (size_t k = 0; k < blocks.size(); ++k) {
+      const ResBlockW& rb = blocks[k];
+      const float* a = arow + k * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m, gate_m
+      ln_modulate(rb.lnc_w, rb.lnc_b, a, a + H, B, L, bufU.p, s);
+      convnext(rb.cn, B, L, a + 2 * H, s);
+      ln_modulate(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
+      gemm(problem(rb.mlp0, bufU.p, H, B, L, L, bufA.p, H, b16, EPI_SILU), rb.mlp0, bf(), s);
+      TapGemm p = problem(rb.mlp2, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
+      p.gate = a + 5 * H; p.gate_bstride = ada_n; p.hres = h.as<float>(); p.ld_res = H;
+      gemm(p, rb.mlp2, bf(), s);
+    }
+    const float* a = arow + blocks.size() * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m
+    ln_modulate(nullptr, nullptr, a, a + H, B, L, bufU.p, s);
+    convnext(fin, B, L, a + 2 * H, s);
+    ln_modulate(nullptr, nullptr, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
+    TapGemm p = problem(conv_out, bufU.p, H, B, L, L, nullptr, D, 0, EPI_EULER);
+    p.hres = target; p.ld_res = D; p.alpha = alpha;
+    gemm(p, conv_out, bf(), s);
+  }
+  int launches_per_step() const { return (bf() ? 2 : 1) + (int)blocks.size() * 9 + 8; }
+
+  bool ensure(int B, int L, int nfe) {
+    const int64_t M = (int64_t)B * L;
+    const size_t e = esize();
+    bool moved = false;
+    moved |= cond_s.ensure(M * D * 4); moved |= spk_s.ensure((size_t)B * cfg.spk_dim * 4);
+    moved |= noise_s.ensure(M * D * 4); moved |= ts_s.ensure((size_t)(nfe + 1) * 4);
+    moved |= x.ensure(M * D * 4); moved |= xb.ensure(M * D * 2); moved |= vout.ensure(M * D * 4);
+    moved |= h.ensure(M * H * 4);
+    moved |= bufU.ensure(M * H * e); moved |= bufD.ensure(M * H * e); moved |= bufG.ensure(M * H * e);
+    moved |= bufA.ensure(M * H * e);
+    moved |= part.ensure((size_t)B * dw_nchunk(L) * H * 2 * 4);
+    moved |= gsc.ensure((size_t)B * H * 4); moved |= gof.ensure((size_t)B * H * 4);
+    moved |= ada.ensure((size_t)nfe * B * ada_n * 4); moved |= sbuf.ensure((size_t)nfe * B * H * e);
+    moved |= temb.ensure((size_t)nfe * H * 4); moved |= tfreq.ensure((size_t)nfe * 256 * 4);
+    moved |= teh.ensure((size_t)nfe * H * 4); moved |= cvec.ensure((size_t)B * H * 4);
+    if (moved) graphs.clear();
+    return moved;
+  }
+};
+
+extern "C" int flm_denoiser_load(flm_ctx* ctx, const flm_tensor* weights, int n, const flm_prob_cfg* cfg, int mode,
+                                 flm_denoiser** out) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && weights && cfg && out, "null argument");
+  FLM_REQUIRE(mode == FLM_F32 || mode == FLM_BF16, "bad mode");
+  FLM_REQUIRE(cfg->hidden_dim % 256 == 0 && cfg->hidden_dim <= 1024, "hidden_dim must be a multiple of 256, <= 1024");
+  FLM_REQUIRE(cfg->target_dim % 64 == 0, "target_dim must be a multiple of 64");
+  set_device(ctx);
+  WeightMap wm(weights, n);
+  std::unique_ptr<flm_denoiser> h(new flm_denoiser(ctx, mode));
+  h->cfg = *cfg;
+  h->load(wm);
+  *out = h.release();
+  FLM_API_END
+}
+extern "C" void flm_denoiser_destroy(flm_denoiser* h) { delete h; }
+extern "C" int flm_denoiser_launches_per_step(flm_denoiser* h) { return h ? h->launches_per_step() : 0; }
+
+extern "C" int flm_cond_prepare(flm_denoiser* h, const float* prior_embs, const uint8_t* mask, int B, int L,
+                                float* out_cond, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && prior_embs && mask && out_cond, "null argument");
+  set_device(h->ctx);
+  if (B == 0 || L == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int Q = h->cfg.n_quantizers, CD = h->cfg.cond_dim;
+  const int64_t M = (int64_t)B * L;
+  int cin = Q * CD;
+  const size_t e = h->esize();
+  const int b16 = h->bf() ? 1 : 0;
+  h->c_xq.ensure(M * cin * e); h->c_xm.ensure(M * cin * e); h->c_h.ensure(M * cin * e);
+  h->c_part.ensure((size_t)B * gs_nchunk(L) * 8 * 2 * 4);
+  h->c_sc.ensure((size_t)B * cin * 4); h->c_of.ensure((size_t)B * cin * 4);
+  launch_quantizer_fold(prior_embs, h->qemb, mask, B, Q, L, CD, h->c_xq.p, h->c_xm.p, b16, s);
+  void* xq = h->c_xq.p;  // current x (unmasked)
+  void* xm = h->c_xm.p;  // GEMM input
+  void* hb = h->c_h.p;
+  for (size_t st = 0; st < h->stages.size(); ++st) {
+    const flm_denoiser::Stage& sg = h->stages[st];
+    if (st > 0)  // configs/prob.yaml uses 1 stage; a second stage needs x*mask of the previous output
+      throw Error(FLM_ERR_UNSUPPORTED, "downsampling_stages > 1 is not implemented");
+    // ResnetBlock1D: x + Mish(GN8(conv(x*m))) * m   (prob_generator.py:11-32)
+    h->gemm(h->problem(sg.conv_a, xm, cin, B, L, L, hb, cin, b16, EPI_NONE), sg.conv_a, h->bf(), s);
+    launch_group_stats(hb, b16, B, L, cin, 8, h->c_part.as<float>(), s);
+    launch_gn_finalize(h->c_part.as<float>(), B, L, cin, 8, gs_nchunk(L), GS_ROWS, sg.gna_w, sg.gna_b, 1e-5f,
+                       h->c_sc.as<float>(), h->c_of.as<float>(), s);
+    GnApply ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.x = hb; ga.x_bf16 = b16; ga.y = xm; ga.y_bf16 = b16; ga.scale = h->c_sc.as<float>(); ga.offset = h->c_of.as<float>();
+    ga.mask = mask; ga.res = xq; ga.res_bf16 = b16; ga.act = 2; ga.B = B; ga.L = L; ga.C = cin;
+    launch_gn_apply(ga, s);
+    // down block: ReLU(GN8(conv(x)))   (prob_generator.py:181-192)
+    h->gemm(h->problem(sg.conv_b, xm, cin, B, L, L, hb, cin / 2, b16, EPI_NONE), sg.conv_b, h->bf(), s);
+    launch_group_stats(hb, b16, B, L, cin / 2, 8, h->c_part.as<float>(), s);
+    launch_gn_finalize(h->c_part.as<float>(), B, L, cin / 2, 8, gs_nchunk(L), GS_ROWS, sg.gnb_w, sg.gnb_b, 1e-5f,
+                       h->c_sc.as<float>(), h->c_of.as<float>(), s);
+    memset(&ga, 0, sizeof(ga));
+    ga.x = hb; ga.x_bf16 = b16; ga.y = xq; ga.y_bf16 = b16; ga.scale = h->c_sc.as<float>(); ga.offset = h->c_of.as<float>();
+    ga.act = 1; ga.B = B; ga.L = L; ga.C = cin / 2;
+    launch_gn_apply(ga, s);
+    cin /= 2;
+  }
+  // proj_out: ReLU(Linear)   (prob_generator.py:194-197)
+  h->gemm(h->problem(h->proj_out, xq, cin, B, L, L, out_cond, h->D, 0, EPI_RELU), h->proj_out, h->bf(), s);
+  FLM_API_END
+}
+
+extern "C" int flm_denoiser_sample(flm_denoiser* h, const float* cond, const float* spk, const float* noise,
+                                   const float* ts_host, int B, int L, int nfe, float temperature, float* out_latents,
+                                   int use_graph, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && cond && spk && noise && ts_host && out_latents, "null argument");
+  FLM_REQUIRE(nfe >= 1, "nfe must be >= 1");
+  set_device(h->ctx);
+  if (B == 0 || L == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int64_t M = (int64_t)B * L;
+  h->ensure(B, L, nfe);
+  FLM_CUDA(cudaMemcpyAsync(h->cond_s.p, cond, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->spk_s.p, spk, (size_t)B * h->cfg.spk_dim * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->noise_s.p, noise, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts_host, (size_t)(nfe + 1) * 4, cudaMemcpyHostToDevice, s));
+  const float dt = (float)(1.0 / nfe);
+  auto body = [&](cudaStream_t cs) {
+    h->modulation_table(B, nfe, cs);
+    launch_noise_init(h->noise_s.as<float>(), h->cond_s.as<float>(), temperature, M * h->D, h->x.as<float>(), cs);
+    for (int i = 0; i < nfe; ++i) h->step(B, L, i, h->x.as<float>(), dt, cs);
+  };
+  if (use_graph) {
+    int tbits;
+    memcpy(&tbits, &temperature, 4);
+    h->graphs.run(std::make_tuple(B, L, nfe, tbits), s, body);
+  } else {
+    body(s);
+  }
+  FLM_CUDA(cudaMemcpyAsync(out_latents, h->x.p, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_API_END
+}
+
+extern "C" int flm_denoiser_forward(flm_denoiser* h, const float* x, const float* spk, float t, int B, int L,
+                                    float* out_v, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && x && spk && out_v, "null argument");
+  set_device(h->ctx);
+  if (B == 0 || L == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int64_t M = (int64_t)B * L;
+  h->ensure(B, L, 1);
+  const float ts[2] = {t, 1.0f};
+  FLM_CUDA(cudaMemcpyAsync(h->x.p, x, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->spk_s.p, spk, (size_t)B * h->cfg.spk_dim * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts, 8, cudaMemcpyHostToDevice, s));
+  FLM_CUDA(cudaMemsetAsync(h->vout.p, 0, M * h->D * 4, s));
+  h->modulation_table(B, 1, s);
+  h->step(B, L, 0, h->vout.as<float>(), 1.0f, s);
+  FLM_CUDA(cudaMemcpyAsync(out_v, h->vout.p, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_API_END
+}
+
+// ===================================================================================== codec
+namespace {
+struct ActW {
+  float *a, *invb;
+  float fu[12], fd[12];
+  int C;
+};
+struct ResUnitW {
+  ActW act1, act2;
+  Layer conv7, conv1;
+};
+
+ActW load_act(WeightStore& store, const WeightMap& wm, const std::string& p, int C) {
+  ActW a;
+  a.C = C;
+  std::vector<float> al = wm.vec(p + ".act.alpha", {C}), be = wm.vec(p + ".act.beta", {C});
+  std::vector<float> ea(C), ib(C);
+  for (int i = 0; i < C; ++i) {
+    ea[i] = expf(al[i]);                          // alpha_logscale (facodec.py:113-114)
+    ib[i] = 1.0f / (expf(be[i]) + 0.000000001f);  // facodec.py:116
+  }
+  a.a = store.upload(ea);
+  a.invb = store.upload(ib);
+  std::vector<float> fu = wm.vec(p + ".upsample.filter", {1, 1, 12});
+  std::vector<float> fd = wm.vec(p + ".downsample.lowpass.filter", {1, 1, 12});
+  for (int i = 0; i < 12; ++i) { a.fu[i] = fu[i]; a.fd[i] = fd[i]; }
+  return a;
+}
+
+Layer load_wn_conv(Engine& e, const WeightMap& wm, const std::string& p, int N, int K, int k, int off0, int dil,
+                   int stride, bool want_bf16) {
+  std::vector<float> w = fold_weight_norm(wm.vec(p + ".weight_g", {N, 1, 1}), wm.vec(p + ".weight_v", {N, K, k}), N);
+  return e.make_layer(pack_conv(w, N, K, k), wm.vec(p + ".bias", {N}), K, N, k, off0, dil, stride, want_bf16);
+}
+
+ResUnitW load_res_unit(Engine& e, const WeightMap& wm, const std::string& p, int C, int dil, bool want_bf16) {
+  ResUnitW r;
+  r.act1 = load_act(e.store, wm, p + ".block.0", C);
+  r.conv7 = load_wn_conv(e, wm, p + ".block.1", C, C, 7, -3 * dil, dil, 1, want_bf16);
+  r.act2 = load_act(e.store, wm, p + ".block.2", C);
+  r.conv1 = load_wn_conv(e, wm, p + ".block.3", C, C, 1, 0, 1, 1, want_bf16);
+  return r;
+}
+
+void run_act(const Engine& e, const ActW& a, const void* x, void* y, int B, int T, cudaStream_t s) {
+  Act1d p;
+  p.x = x; p.y = y; p.io_bf16 = e.bf() ? 1 : 0; p.a = a.a; p.invb = a.invb;
+  memcpy(p.fu, a.fu, sizeof(p.fu));
+  memcpy(p.fd, a.fd, sizeof(p.fd));
+  p.B = B; p.T = T; p.C = a.C; p.fast_sin = e.bf() ? 1 : 0;
+  launch_act1d(p, s);
+}
+
+// x <- x + conv1(act(conv7(act(x))))   (facodec.py:121-133); t1,t2 scratch
+void run_res_unit(const Engine& e, const ResUnitW& r, void* x, void* t1, void* t2, int B, int T, cudaStream_t s) {
+  const int C = r.act1.C, b16 = e.bf() ? 1 : 0;
+  run_act(e, r.act1, x, t1, B, T, s);
+  e.gemm(e.problem(r.conv7, t1, C, B, T, T, t2, C, b16, EPI_NONE), r.conv7, e.bf(), s);
+  run_act(e, r.act2, t2, t1, B, T, s);
+  TapGemm p = e.problem(r.conv1, t1, C, B, T, T, x, C, b16, EPI_RESID);
+  p.resid_in = x;
+  e.gemm(p, r.conv1, e.bf(), s);
+}
+}  // namespace
+
+struct flm_codec_dec : Engine {
+  Layer timbre_linear, conv0;
+  struct Block { ActW act; Layer up; int stride, cin, cout; ResUnitW ru[3]; };
+  std::vector<Block> blocks;
+  ActW act_out;
+  float* wout; float bout; int cout_final;
+  std::map<std::string, ActW> acts_by_name;
+  DevBuf style, buf[3], tbuf;
+  flm_codec_dec(flm_ctx* c, int mode) : Engine(c, mode) {}
+};
+
+extern "C" int flm_codec_dec_load(flm_ctx* ctx, const flm_tensor* weights, int n, int mode, flm_codec_dec** out) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && weights && out, "null argument");
+  FLM_REQUIRE(mode == FLM_F32 || mode == FLM_BF16, "bad mode");
+  set_device(ctx);
+  WeightMap wm(weights, n);
+  std::unique_ptr<flm_codec_dec> h(new flm_codec_dec(ctx, mode));
+  const bool b = h->bf();
+  const flm_tensor& w0 = wm.get("model.0.weight_v");
+  const int C0 = (int)w0.shape[0], Cin = (int)w0.shape[1];
+  FLM_REQUIRE(w0.ndim == 3 && w0.shape[2] == 7, "model.0 must be a k=7 conv");
+  h->timbre_linear = h->make_layer(wm.vec("timbre_linear.weight", {2 * Cin, Cin}), wm.vec("timbre_linear.bias", {2 * Cin}),
+                                   Cin, 2 * Cin, 1, 0, 1, 1, false);
+  h->conv0 = load_wn_conv(*h, wm, "model.0", C0, Cin, 7, -3, 1, 1, b);
+  int c = C0, i = 1;
+  while (wm.has("model." + std::to_string(i) + ".block.1.weight_v")) {
+    const std::string p = "model." + std::to_string(i);
+    const flm_tensor& wv = wm.get(p + ".block.1.weight_v");  // (Cin, Cout, 2s)
+    flm_codec_dec::Block blk;
+    blk.cin = (int)wv.shape[0]; blk.cout = (int)wv.shape[1]; blk.stride = (int)wv.shape[2] / 2;
+    FLM_REQUIRE(blk.cin == c, "decoder block channel mismatch");
+    blk.act = load_act(h->store, wm, p + ".block.0", blk.cin);
+    h->acts_by_name[p + ".block.0"] = blk.act;
+    std::vector<float> w = fold_weight_norm(wm.vec(p + ".block.1.weight_g", {blk.cin, 1, 1}),
+                                            wm.vec(p + ".block.1.weight_v", {blk.cin, blk.cout, 2 * blk.stride}), blk.cin);
+    blk.up = h->make_layer(pack_conv_transpose(w, blk.cin, blk.cout, blk.stride),
+                           replicate(wm.vec(p + ".block.1.bias", {blk.cout}), blk.stride), blk.cin,
+                           blk.stride * blk.cout, 3, -1, 1, 1, b);
+    const int dils[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) {
+      const std::string rp = p + ".block." + std::to_string(j + 2);
+      blk.ru[j] = load_res_unit(*h, wm, rp, blk.cout, dils[j], b);
+      h->acts_by_name[rp + ".block.0"] = blk.ru[j].act1;
+      h->acts_by_name[rp + ".block.2"] = blk.ru[j].act2;
+    }
+    h->blocks.push_back(blk);
+    c = blk.cout;
+    ++i;
+  }
+  FLM_REQUIRE(!h->blocks.empty(), "no decoder blocks found (model.1.block.1.weight_v missing)");
+  const std::string pa = "model." + std::to_string(i), pc = "model." + std::to_string(i + 1);
+  h->act_out = load_act(h->store, wm, pa, c);
+  h->acts_by_name[pa] = h->act_out;
+  std::vector<float> w = fold_weight_norm(wm.vec(pc + ".weight_g", {1, 1, 1}), wm.vec(pc + ".weight_v", {1, c, 7}), 1);
+  std::vector<float> wt((size_t)7 * c);
+  for (int ch = 0; ch < c; ++ch)
+    for (int t = 0; t < 7; ++t) wt[(size_t)t * c + ch] = w[(size_t)ch * 7 + t];
+  h->wout = h->store.upload(wt);
+  h->bout = wm.vec(pc + ".bias", {1})[0];
+  h->cout_final = c;
+  *out = h.release();
+  FLM_API_END
+}
+extern "C" void flm_codec_dec_destroy(flm_codec_dec* h) { delete h; }
+
+extern "C" int flm_codec_decode(flm_codec_dec* h, const float* latents, const float* spk, int B, int L, float* out_wav,
+                                flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && latents && spk && out_wav, "null argument");
+  set_device(h->ctx);
+  if (B == 0 || L == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int Cin = h->conv0.K, b16 = h->bf() ? 1 : 0;
+  const size_t e = h->esize();
+  // largest activation: elements per latent frame
+  int64_t per_frame = std::max<int64_t>(h->conv0.N, Cin);
+  {
+    int64_t rate = 1;
+    for (auto& blk : h->blocks) { rate *= blk.stride; per_frame = std::max<int64_t>(per_frame, rate * blk.cout); }
+  }
+  for (int k = 0; k < 3; ++k) h->buf[k].ensure((size_t)B * L * per_frame * e);
+  h->style.ensure((size_t)B * 2 * Cin * 4);
+  void *x = h->buf[0].p, *t1 = h->buf[1].p, *t2 = h->buf[2].p;
+  // style = timbre_linear(spk); x = LN_noaffine(latents) * gamma + beta   (facodec.py:631-636)
+  h->gemm(h->problem(h->timbre_linear, spk, Cin, 1, B, B, h->style.p, 2 * Cin, 0, EPI_NONE), h->timbre_linear, false, s);
+  LnMod ln;
+  memset(&ln, 0, sizeof(ln));
+  ln.x = latents; ln.ldx = Cin; ln.y = t1; ln.ldy = Cin; ln.y_bf16 = b16;
+  ln.scale = h->style.as<float>(); ln.shift = h->style.as<float>() + Cin; ln.mod_bstride = 2 * Cin; ln.scale_plus_one = 0.f;
+  ln.eps = 1e-5f; ln.rows = (int64_t)B * L; ln.rows_per_batch = L; ln.C = Cin;
+  launch_ln_mod(ln, s);
+  h->gemm(h->problem(h->conv0, t1, Cin, B, L, L, x, h->conv0.N, b16, EPI_NONE), h->conv0, h->bf(), s);
+  int T = L;
+  for (auto& blk : h->blocks) {
+    run_act(*h, blk.act, x, t1, B, T, s);
+    // transposed conv: (B,T,cin) -> (B,T,s*cout) == (B,T*s,cout)
+    h->gemm(h->problem(blk.up, t1, blk.cin, B, T, T, t2, blk.up.N, b16, EPI_NONE), blk.up, h->bf(), s);
+    std::swap(x, t2);
+    T *= blk.stride;
+    for (int j = 0; j < 3; ++j) run_res_unit(*h, blk.ru[j], x, t1, t2, B, T, s);
+  }
+  run_act(*h, h->act_out, x, t1, B, T, s);
+  launch_conv_out_tanh(t1, b16, h->wout, h->bout, B, T, h->cout_final, out_wav, s);
+  FLM_API_END
+}
+
+extern "C" int flm_codec_dec_activation(flm_codec_dec* h, const char* prefix, const float* x, int B, int T, int C,
+                                        float* y, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && prefix && x && y, "null argument");
+  set_device(h->ctx);
+  auto it = h->acts_by_name.find(prefix);
+  if (it == h->acts_by_name.end()) throw Error(FLM_ERR_ARG, std::string("no activation named ") + prefix);
+  FLM_REQUIRE(it->second.C == C, "channel count mismatch");
+  Act1d p;
+  p.x = x; p.y = y; p.io_bf16 = 0; p.a = it->second.a; p.invb = it->second.invb;
+  memcpy(p.fu, it->second.fu, sizeof(p.fu));
+  memcpy(p.fd, it->second.fd, sizeof(p.fd));
+  p.B = B; p.T = T; p.C = C; p.fast_sin = 0;
+  launch_act1d(p, S(stream));
+  FLM_API_END
+}
+
+// ---- encoder (fp32 FMA; runs once per distinct prompt)
+struct flm_codec_enc : Engine {
+  float *w_in, *b_in; int c_in;
+  struct Block { ResUnitW ru[3]; ActW act; Layer down; int stride, pad; };
+  std::vector<Block> blocks;
+  ActW act_out;
+  Layer conv_out;
+  DevBuf buf[3];
+  flm_codec_enc(flm_ctx* c) : Engine(c, FLM_F32) {}
+};
+
+extern "C" int flm_codec_enc_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_codec_enc** out) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && weights && out, "null argument");
+  set_device(ctx);
+  WeightMap wm(weights, n);
+  std::unique_ptr<flm_codec_enc> h(new flm_codec_enc(ctx));
+  const flm_tensor& w0 = wm.get("block.0.weight_v");
+  const int C0 = (int)w0.shape[0];
+  FLM_REQUIRE(w0.ndim == 3 && w0.shape[1] == 1 && w0.shape[2] == 7, "block.0 must be a 1->C k=7 conv");
+  {
+    std::vector<float> w = fold_weight_norm(wm.vec("block.0.weight_g", {C0, 1, 1}), wm.vec("block.0.weight_v", {C0, 1, 7}), C0);
+    std::vector<float> wt((size_t)7 * C0);
+    for (int c = 0; c < C0; ++c)
+      for (int t = 0; t < 7; ++t) wt[(size_t)t * C0 + c] = w[(size_t)c * 7 + t];
+    h->w_in = h->store.upload(wt);
+    h->b_in = h->store.upload(wm.vec("block.0.bias", {C0}));
+    h->c_in = C0;
+  }
+  int c = C0, i = 1;
+  while (wm.has("block." + std::to_string(i) + ".block.4.weight_v")) {
+    const std::string p = "block." + std::to_string(i);
+    const flm_tensor& wv = wm.get(p + ".block.4.weight_v");  // (2c, c, 2s)
+    flm_codec_enc::Block blk;
+    blk.stride = (int)wv.shape[2] / 2;
+    blk.pad = blk.stride / 2 + blk.stride % 2;
+    FLM_REQUIRE((int)wv.shape[1] == c, "encoder block channel mismatch");
+    const int dils[3] = {1, 3, 9};
+    for (int j = 0; j < 3; ++j) blk.ru[j] = load_res_unit(*h, wm, p + ".block." + std::to_string(j), c, dils[j], false);
+    blk.act = load_act(h->store, wm, p + ".block.3", c);
+    const int cn = (int)wv.shape[0];
+    blk.down = load_wn_conv(*h, wm, p + ".block.4", cn, c, 2 * blk.stride, -blk.pad, 1, blk.stride, false);
+    h->blocks.push_back(blk);
+    c = cn;
+    ++i;
+  }
+  FLM_REQUIRE(!h->blocks.empty(), "no encoder blocks found");
+  const std::string pa = "block." + std::to_string(i), pc = "block." + std::to_string(i + 1);
+  h->act_out = load_act(h->store, wm, pa, c);
+  const flm_tensor& wo = wm.get(pc + ".weight_v");
+  h->conv_out = load_wn_conv(*h, wm, pc, (int)wo.shape[0], c, 3, -1, 1, 1, false);
+  *out = h.release();
+  FLM_API_END
+}
+extern "C" void flm_codec_enc_destroy(flm_codec_enc* h) { delete h; }
+
+extern "C" int64_t flm_codec_enc_frames(flm_codec_enc* h, int64_t S_) {
+  if (!h) return -1;
+  int64_t T = S_;
+  for (auto& blk : h->blocks) {
+    const int64_t num = T + 2 * blk.pad - 2 * blk.stride;
+    if (num < 0) return 0;
+    T = num / blk.stride + 1;
+  }
+  return T;
+}
+
+extern "C" int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S_, float* out, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && wav && out, "null argument");
+  set_device(h->ctx);
+  const int64_t Tout = flm_codec_enc_frames(h, S_);
+  FLM_REQUIRE(Tout > 0, "prompt too short for the encoder");
+  FLM_REQUIRE(S_ < (1ll << 30), "prompt too long");
+  if (B == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  // largest activation: first stage S x C0 (channels double while T shrinks by >= 2)
+  size_t mx = (size_t)S_ * h->c_in;
+  {
+    int64_t T = S_;
+    for (auto& blk : h->blocks) {
+      T = (T + 2 * blk.pad - 2 * blk.stride) / blk.stride + 1;
+      mx = std::max(mx, (size_t)T * blk.down.N);
+    }
+  }
+  for (int k = 0; k < 3; ++k) h->buf[k].ensure((size_t)B * mx * 4);
+  void *x = h->buf[0].p, *t1 = h->buf[1].p, *t2 = h->buf[2].p;
+  launch_conv_in_wav(wav, h->w_in, h->b_in, B, S_, h->c_in, static_cast<float*>(x), s);
+  int T = (int)S_;
+  for (auto& blk : h->blocks) {
+    for (int j = 0; j < 3; ++j) run_res_unit(*h, blk.ru[j], x, t1, t2, B, T, s);
+    run_act(*h, blk.act, x, t1, B, T, s);
+    const int Tn = (T + 2 * blk.pad - 2 * blk.stride) / blk.stride + 1;
+    h->gemm(h->problem(blk.down, t1, blk.down.K, B, T, Tn, t2, blk.down.N, 0, EPI_NONE), blk.down, false, s);
+    std::swap(x, t2);
+    T = Tn;
+  }
+  run_act(*h, h->act_out, x, t1, B, T, s);
+  h->gemm(h->problem(h->conv_out, t1, h->conv_out.K, B, T, T, t2, h->conv_out.N, 0, EPI_NONE), h->conv_out, false, s);
+  launch_transpose_out(static_cast<const float*>(t2), B, T, h->conv_out.N, out, s);
+  FLM_API_END
+}
+
+// ===================================================================================== test hook
+extern "C" int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, const float* bias, int B,
+                                int T_in, int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi,
+                                float* out, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && A && W && out, "null argument");
+  FLM_REQUIRE(epi >= 0 && epi <= EPI_RELU, "epi must be 0..3");
+  set_device(ctx);
+  cudaStream_t s = S(stream);
+  TapGemm p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias; p.out = out; p.lda = K; p.ldc = N; p.B = B; p.T_in = T_in; p.T_out = T_out; p.K = K; p.N = N;
+  p.ntaps = ntaps; p.off0 = off0; p.dil = dil; p.stride = stride; p.epi = epi; p.out_bf16 = 0;
+  if (mode == FLM_F32) {
+    p.A = A; p.W = W;
+    launch_tapgemm_simt(p, s);
+  } else {
+    DevBuf a16, w16;
+    const int64_t na = (int64_t)B * T_in * K, nw = (int64_t)ntaps * N * K;
+    a16.ensure(na * 2); w16.ensure(nw * 2);
+    launch_f32_to_bf16(A, a16.as<bf16>(), na, s);
+    launch_f32_to_bf16(W, w16.as<bf16>(), nw, s);
+    p.A = a16.p; p.W = w16.p;
+    launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
+    FLM_CUDA(cudaStreamSynchronize(s));  // a16/w16 are freed on return
+  }
+  FLM_API_END
+}

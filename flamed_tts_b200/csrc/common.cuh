@@ -1,0 +1,144 @@
+// Shared device/host helpers for the flamed_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+namespace flm {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FLM_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw flm::Error(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                               std::to_string(__LINE__) + ")");                                     \
+  } while (0)
+
+#define FLM_REQUIRE(cond, msg)                                                  \
+  do {                                                                          \
+    if (!(cond)) throw flm::Error(-1, std::string("argument error: ") + (msg)); \
+  } while (0)
+
+#define FLM_LAUNCH_CHECK() FLM_CUDA(cudaGetLastError())
+
+// ---- element access in storage type T (float or bf16), arithmetic always fp32
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) {
+  return *p;
+}
+template <>
+__device__ __forceinline__ float ldf<bf16>(const bf16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void stf<bf16>(bf16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// 4 consecutive elements (16 B fp32 / 8 B bf16), pointer must be aligned accordingly
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void ld4<bf16>(const bf16* p, float (&v)[4]) {
+  uint2 t = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+  v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void st4<bf16>(bf16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&a);
+  t.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- activations (exact forms used by the reference)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float mish(float x) {
+  float sp = x > 20.0f ? x : log1pf(expf(x));  // F.softplus threshold 20
+  return x * tanhf(sp);
+}
+
+enum Epi : int {
+  EPI_NONE = 0,
+  EPI_GELU = 1,
+  EPI_SILU = 2,
+  EPI_RELU = 3,
+  EPI_RESID = 4,       // out = resid_in + v                      (codec ResidualUnit skip)
+  EPI_GATE_RESID = 5,  // hres = hres + gate[b,n] * (v + addend)  (adaLN-gated residual, fp32 stream)
+  EPI_EULER = 6,       // hres = hres + alpha * v                 (x_t += dt * v)
+};
+
+// Implicit-conv GEMM problem (see include/flamed_b200.h: flm_tapgemm_test)
+struct TapGemm {
+  const void* A;   // (B, T_in, K) storage type TA, row stride lda elements
+  const void* W;   // (ntaps, N, K) storage type TA
+  const float* bias;  // (N) or null
+  void* out;       // (B, T_out, N) row stride ldc elements; may be null for GATE_RESID / EULER
+  int64_t lda, ldc;
+  int B, T_in, T_out, K, N;
+  int ntaps, off0, dil, stride;
+  int epi;
+  int out_bf16;    // 0: out is float, 1: out is bf16
+  // epilogue operands
+  const float* gate;     // gate[b * gate_bstride + n]
+  int64_t gate_bstride;
+  const void* addend;    // (B,T_out,N) storage type = A's, row stride ld_add (inner ConvNeXt residual u)
+  int64_t ld_add;
+  int addend_bf16;
+  float* hres;           // fp32 residual stream (B,T_out,N), row stride ld_res, updated in place
+  int64_t ld_res;
+  const void* resid_in;  // EPI_RESID: (B,T_out,N) same storage type as out, row stride ldc
+  float alpha;
+};
+
+// value after bias -> final value; handles every epilogue except the memory side effects
+__device__ __forceinline__ float epi_act(int epi, float v) {
+  switch (epi) {
+    case EPI_GELU: return gelu_erf(v);
+    case EPI_SILU: return silu(v);
+    case EPI_RELU: return fmaxf(v, 0.0f);
+    default: return v;
+  }
+}
+
+}  // namespace flm

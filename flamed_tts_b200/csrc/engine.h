@@ -1,0 +1,222 @@
+// Host-side runtime pieces shared by the module handles: context, device buffers, weight
+// lookup / packing, GEMM dispatch (fp32 FMA vs tcgen05) and the CUDA-graph cache.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flamed_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+struct flm_ctx {
+  int device = 0;
+  int num_sms = 0;
+  void* tma_encode = nullptr;  // cuTensorMapEncodeTiled
+};
+
+namespace flm {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  // grow-only; returns true if the pointer changed (callers drop cached graphs then)
+  bool ensure(size_t n) {
+    if (n <= bytes) return false;
+    if (p) FLM_CUDA(cudaFree(p));
+    p = nullptr; bytes = 0;
+    FLM_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+    return true;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// owns every packed weight of a module
+struct WeightStore {
+  std::vector<void*> ptrs;
+  ~WeightStore() { for (void* p : ptrs) cudaFree(p); }
+  float* upload(const std::vector<float>& v) {
+    void* d = nullptr;
+    FLM_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+    ptrs.push_back(d);
+    if (!v.empty()) FLM_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return static_cast<float*>(d);
+  }
+  bf16* upload_bf16(const std::vector<float>& v) {
+    std::vector<bf16> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16_rn(v[i]);
+    void* d = nullptr;
+    FLM_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(bf16)));
+    ptrs.push_back(d);
+    if (!v.empty()) FLM_CUDA(cudaMemcpy(d, h.data(), v.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+    return static_cast<bf16*>(d);
+  }
+};
+
+struct WeightMap {
+  std::unordered_map<std::string, const flm_tensor*> m;
+  WeightMap(const flm_tensor* w, int n) {
+    for (int i = 0; i < n; ++i) m[w[i].name] = &w[i];
+  }
+  bool has(const std::string& k) const { return m.count(k) != 0; }
+  const flm_tensor& get(const std::string& k) const {
+    auto it = m.find(k);
+    if (it == m.end()) throw Error(FLM_ERR_WEIGHT, "missing weight: " + k);
+    return *it->second;
+  }
+  static int64_t numel(const flm_tensor& t) {
+    int64_t n = 1;
+    for (int i = 0; i < t.ndim; ++i) n *= t.shape[i];
+    return n;
+  }
+  // host copy, checking the expected shape
+  std::vector<float> vec(const std::string& k, std::initializer_list<int64_t> shape) const {
+    const flm_tensor& t = get(k);
+    if ((size_t)t.ndim != shape.size()) throw Error(FLM_ERR_WEIGHT, "bad rank for " + k);
+    int i = 0;
+    for (int64_t s : shape) {
+      if (s >= 0 && t.shape[i] != s)
+        throw Error(FLM_ERR_WEIGHT, "bad shape for " + k + ": dim " + std::to_string(i) + " is " +
+                                        std::to_string(t.shape[i]) + ", expected " + std::to_string(s));
+      ++i;
+    }
+    return std::vector<float>(t.data, t.data + numel(t));
+  }
+};
+
+// a dense / conv layer in tap-GEMM form
+struct Layer {
+  int K = 0, N = 0, ntaps = 1, off0 = 0, dil = 1, stride = 1;
+  float* w32 = nullptr;  // (ntaps, N, K)
+  bf16* w16 = nullptr;   // same, bf16 (only when the module runs in FLM_BF16)
+  float* bias = nullptr; // (N)
+};
+
+// torch weight_norm (old style): w = g * v / ||v||, norm over all dims but 0 (facodec.py:27-32)
+inline std::vector<float> fold_weight_norm(const std::vector<float>& g, const std::vector<float>& v, int64_t dim0) {
+  const int64_t inner = (int64_t)v.size() / dim0;
+  std::vector<float> w(v.size());
+  for (int64_t i = 0; i < dim0; ++i) {
+    double s = 0;
+    for (int64_t j = 0; j < inner; ++j) s += (double)v[i * inner + j] * v[i * inner + j];
+    const float scale = (float)((double)g[i] / std::sqrt(s));
+    for (int64_t j = 0; j < inner; ++j) w[i * inner + j] = v[i * inner + j] * scale;
+  }
+  return w;
+}
+
+// Conv1d weight (N, K, k) -> tap-major (k, N, K)
+inline std::vector<float> pack_conv(const std::vector<float>& w, int N, int K, int k) {
+  std::vector<float> o((size_t)k * N * K);
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < K; ++c)
+      for (int t = 0; t < k; ++t) o[((size_t)t * N + n) * K + c] = w[((size_t)n * K + c) * k + t];
+  return o;
+}
+
+// ConvTranspose1d weight (Cin, Cout, 2s), stride s, padding p = s/2 + s%2, output_padding s%2
+// (facodec.py:246-265) as a 3-tap conv with s*Cout output columns: out row q holds the s output
+// frames q*s + r;  out[q*s+r, co] = sum_{d in {1,0,-1}} sum_ci x[q-d, ci] * w[ci, co, s*d + r + p]
+inline std::vector<float> pack_conv_transpose(const std::vector<float>& w, int Cin, int Cout, int s) {
+  const int k = 2 * s, p = s / 2 + s % 2;
+  std::vector<float> o((size_t)3 * s * Cout * Cin, 0.f);
+  for (int tap = 0; tap < 3; ++tap) {
+    const int d = 1 - tap;  // tap 0 reads x[q-1]
+    for (int r = 0; r < s; ++r) {
+      const int kk = s * d + r + p;
+      if (kk < 0 || kk >= k) continue;
+      for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+          o[(((size_t)tap * s + r) * Cout + co) * Cin + ci] = w[((size_t)ci * Cout + co) * k + kk];
+    }
+  }
+  return o;
+}
+
+struct Engine {
+  flm_ctx* ctx;
+  int mode;
+  WeightStore store;
+  Engine(flm_ctx* c, int m) : ctx(c), mode(m) {}
+  bool bf() const { return mode == FLM_BF16; }
+  size_t esize() const { return bf() ? 2 : 4; }
+
+  Layer make_layer(const std::vector<float>& w_packed, const std::vector<float>& bias, int K, int N, int ntaps,
+                   int off0, int dil, int stride, bool want_bf16) {
+    Layer l;
+    l.K = K; l.N = N; l.ntaps = ntaps; l.off0 = off0; l.dil = dil; l.stride = stride;
+    l.w32 = store.upload(w_packed);
+    if (want_bf16) l.w16 = store.upload_bf16(w_packed);
+    l.bias = store.upload(bias);
+    return l;
+  }
+
+  // base problem for a layer: A (B,T_in,K) -> out (B,T_out,N); caller fills the epilogue
+  TapGemm problem(const Layer& l, const void* A, int64_t lda, int B, int T_in, int T_out, void* out, int64_t ldc,
+                  int out_bf16, int epi) const {
+    TapGemm p;
+    memset(&p, 0, sizeof(p));
+    p.A = A; p.lda = lda; p.W = nullptr; p.bias = l.bias; p.out = out; p.ldc = ldc;
+    p.B = B; p.T_in = T_in; p.T_out = T_out; p.K = l.K; p.N = l.N;
+    p.ntaps = l.ntaps; p.off0 = l.off0; p.dil = l.dil; p.stride = l.stride;
+    p.epi = epi; p.out_bf16 = out_bf16;
+    return p;
+  }
+  // fp32 FMA kernel (A fp32) or tcgen05 kernel (A bf16), chosen by `a_bf16`
+  void gemm(TapGemm p, const Layer& l, bool a_bf16, cudaStream_t s) const {
+    if (a_bf16) {
+      if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");
+      p.W = l.w16;
+      launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
+    } else {
+      p.W = l.w32;
+      launch_tapgemm_simt(p, s);
+    }
+  }
+};
+
+// CUDA-graph cache: body(stream) is captured once per key and replayed afterwards
+struct GraphCache {
+  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> execs;
+  ~GraphCache() { clear(); }
+  void clear() {
+    for (auto& kv : execs) cudaGraphExecDestroy(kv.second);
+    execs.clear();
+  }
+  void run(std::tuple<int, int, int, int> key, cudaStream_t stream, const std::function<void(cudaStream_t)>& body) {
+    auto it = execs.find(key);
+    if (it == execs.end()) {
+      cudaGraph_t graph = nullptr;
+      FLM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+      try {
+        body(stream);
+      } catch (...) {
+        cudaStreamEndCapture(stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      FLM_CUDA(cudaStreamEndCapture(stream, &graph));
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      FLM_CUDA(e);
+      it = execs.emplace(key, exec).first;
+    }
+    FLM_CUDA(cudaGraphLaunch(it->second, stream));
+  }
+};
+
+}  // namespace flm

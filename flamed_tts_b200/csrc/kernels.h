@@ -1,0 +1,120 @@
+// Host-side launchers of every kernel in the library (all enqueue on `stream`, never sync).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace flm {
+
+// ---- GEMMs
+void launch_tapgemm_simt(const TapGemm& p, cudaStream_t stream);
+// tcgen05 + TMA path: A/W bf16, K % 64 == 0, N % 64 == 0, stride == 1.  `tma_encode` is the
+// driver's cuTensorMapEncodeTiled entry point (resolved once per context).
+void launch_tapgemm_tc(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream);
+bool tapgemm_tc_supported(const TapGemm& p);
+void tapgemm_tc_init();
+
+// ---- row-wise LayerNorm (+ adaLN modulate): one warp per row, C % 128 == 0, C <= 1024
+// y = LN(x; w, b, eps) * (scale_plus_one + scale[bi]) + shift[bi],  bi = row / rows_per_batch
+struct LnMod {
+  const float* x; int64_t ldx;  // fp32 input rows
+  void* y; int64_t ldy; int y_bf16;
+  const float* w; const float* b;  // affine (nullable)
+  const float* shift; const float* scale; int64_t mod_bstride;  // per-sample modulation (nullable)
+  float scale_plus_one;  // 1 for adaLN `x*(1+scale)+shift`, 0 for plain `x*gamma+beta`
+  float eps;
+  int64_t rows; int rows_per_batch; int C;
+  int relu_in;  // apply ReLU to x before the statistics (durgen: LN(ReLU(conv)))
+};
+void launch_ln_mod(const LnMod& p, cudaStream_t stream);
+
+// ---- depthwise conv k<=31 over time (channels-last) + per-(b,chunk,c) partial statistics
+struct DwConv {
+  const void* x; void* y; int io_bf16;  // (B,L,C)
+  const float* w;   // (KW, C) tap-major
+  const float* bias;  // (C)
+  float* part;      // (B, nchunk, C, 2) = (mean, M2) of each chunk of DW_TT outputs
+  int B, L, C, KW;
+};
+constexpr int DW_TT = 32;
+inline int dw_nchunk(int L) { return (L + DW_TT - 1) / DW_TT; }
+void launch_dwconv(const DwConv& p, cudaStream_t stream);
+
+// ---- generic grouped statistics over (rows x channels-in-group) for GroupNorm(G) in the cond
+//      down-sampler: partials (B, nchunk, G, 2) from chunks of GS_ROWS rows
+constexpr int GS_ROWS = 32;
+inline int gs_nchunk(int L) { return (L + GS_ROWS - 1) / GS_ROWS; }
+void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, float* part, cudaStream_t stream);
+
+// ---- merge partials (Chan) -> per-(b,c) scale = gamma*rstd, offset = beta - mean*scale
+// chunk_rows = rows per chunk, group_size = channels per group (1 for GroupNorm(C,C))
+void launch_gn_finalize(const float* part, int B, int L, int C, int G, int nchunk, int chunk_rows,
+                        const float* gamma, const float* beta, float eps, float* scale, float* offset,
+                        cudaStream_t stream);
+
+// ---- y = act(x*scale[b,c] + offset[b,c]) (*mask[b,t]) (+ res)   act: 0 none, 1 relu, 2 mish
+struct GnApply {
+  const void* x; int x_bf16;
+  void* y; int y_bf16;
+  const float* scale; const float* offset;  // (B,C)
+  const uint8_t* mask;   // (B,L) nullable, 1 = keep
+  const void* res; int res_bf16;  // nullable residual added after masking
+  int act;
+  int B, L, C;
+};
+void launch_gn_apply(const GnApply& p, cudaStream_t stream);
+
+// ---- denoiser small pieces
+// emb (n, 256) = [cos(t_i f_k), sin(t_i f_k)], f_k = exp(-ln(1e4) k / 128)   (prob_generator.py:48-67)
+void launch_timestep_embedding(const float* ts, int n, int dim, float* out, cudaStream_t stream);
+// s[(i*B+b), c] = silu(temb[i,c] + cvec[b,c])
+void launch_silu_sum(const float* temb, const float* cvec, int nfe, int B, int C, void* out, int out_bf16,
+                     cudaStream_t stream);
+// x0 = noise * temperature + cond  (prob_generator.py:440); also writes a bf16 copy if xb != null
+void launch_noise_init(const float* noise, const float* cond, float temperature, int64_t n, float* x, cudaStream_t s);
+void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+
+// ---- cond down-sampler front end: xq[b,l,q*D+d] = prior[b,q,l,d] + qemb[q,d]; xm = xq * mask
+void launch_quantizer_fold(const float* prior, const float* qemb, const uint8_t* mask, int B, int Q, int L, int D,
+                           void* xq, void* xm, int out_bf16, cudaStream_t stream);
+
+// ---- duration generator pieces
+// emb (n, dim) = [sin(1000 t_i f_k), cos(...)], f_k = exp(-k ln(1e4)/(dim/2-1))   (pva.py:9-22)
+void launch_sinusoidal_pos_emb(const float* ts, int n, int dim, float* out, cudaStream_t stream);
+// a0[r,c] = encp[r,c] + xt[r]*w0[c] + temb[c]
+void launch_durgen_input(const float* encp, const float* xt, const float* w0, const float* temb, int64_t rows, int C,
+                         float* out, cudaStream_t stream);
+// v = LN(relu(x); w,b) . wl + bl ; masked -> 0 ; xt += dt * v   (pva.py:217-236, 106/109)
+void launch_durgen_head(const float* x, int64_t rows, int C, const float* lnw, const float* lnb, const float* wl,
+                        const float* bl, const uint8_t* mask, float dt, float* xt, cudaStream_t stream);
+// out = clamp(round(exp(x) - 1), 0)   (pva.py:111-112)
+void launch_duration_round(const float* x, int64_t n, float* out, cudaStream_t stream);
+void launch_scale(const float* x, float s, int64_t n, float* out, cudaStream_t stream);
+
+// ---- length regulator
+void launch_lr_plan(const float* phone, const float* sil, const int64_t* src_lens, int B, int P, int32_t* cumsum,
+                    int64_t* tgt_len, cudaStream_t stream);
+void launch_lr_expand(const float* x, const int32_t* cumsum, int B, int P, int H, int Tmax, float* out,
+                      int32_t* out_index, cudaStream_t stream);
+
+// ---- codec
+struct Act1d {
+  const void* x; void* y; int io_bf16;  // (B,T,C)
+  const float* a;     // exp(alpha) (C)
+  const float* invb;  // 1/(exp(beta)+1e-9) (C)
+  float fu[12], fd[12];  // up / down 12-tap filters
+  int B, T, C;
+  int fast_sin;  // 1: __sinf (bf16 mode), 0: sinf
+};
+void launch_act1d(const Act1d& p, cudaStream_t stream);
+// wav[b,t] = tanh(sum_tap sum_c x[b,t+tap-3,c] w[tap][c] + bias)
+void launch_conv_out_tanh(const void* x, int x_bf16, const float* w, float bias, int B, int T, int C, float* wav,
+                          cudaStream_t stream);
+// y[b,t,c] = sum_tap w[tap][c] * wav[b,t+tap-3] + bias[c]   (encoder first conv, 1 -> C)
+void launch_conv_in_wav(const float* wav, const float* w, const float* bias, int B, int64_t T, int C, float* y,
+                        cudaStream_t stream);
+// (B,T,C) -> (B,C,T)
+void launch_transpose_out(const float* x, int B, int T, int C, float* y, cudaStream_t stream);
+
+}  // namespace flm

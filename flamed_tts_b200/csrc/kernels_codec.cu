@@ -1,0 +1,260 @@
+// FaCodec memory-bound kernels (channels-last): the anti-aliased Snake activation, the 64->1
+// output conv + tanh, the 1->32 input conv of the encoder and the final layout transpose.
+//
+// Reference: flamed/models/facodec/alias_free_torch/act.py:24-29, resample.py:28-37,54-57,
+// filter.py:89-96, facodec.py:105-118 (SnakeBeta); closed form in SURVEY.md Appendix A1:
+//   u[2n]   = 2*sum_{j<6} x[clamp(n-3+j)] * fu[11-2j]
+//   u[2n+1] = 2*sum_{j<6} x[clamp(n-2+j)] * fu[10-2j]
+//   s[m]    = u[m] + sin^2(a*u[m]) * invb
+//   y[n]    = sum_{k<12} s[clamp(2n+k-5, 0, 2T-1)] * fd[k]
+#include "common.cuh"
+#include "kernels.h"
+
+namespace flm {
+
+namespace {
+
+constexpr int ACT_TT = 16;  // outputs per thread along time
+
+template <typename T>
+__device__ __forceinline__ void ldpair(const T* p, float& a, float& b);
+template <>
+__device__ __forceinline__ void ldpair<float>(const float* p, float& a, float& b) {
+  float2 t = *reinterpret_cast<const float2*>(p);
+  a = t.x; b = t.y;
+}
+template <>
+__device__ __forceinline__ void ldpair<bf16>(const bf16* p, float& a, float& b) {
+  __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(p);
+  a = __low2float(t); b = __high2float(t);
+}
+template <typename T>
+__device__ __forceinline__ void stpair(T* p, float a, float b);
+template <>
+__device__ __forceinline__ void stpair<float>(float* p, float a, float b) {
+  *reinterpret_cast<float2*>(p) = make_float2(a, b);
+}
+template <>
+__device__ __forceinline__ void stpair<bf16>(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <bool FAST>
+__device__ __forceinline__ float snake(float u, float a, float invb) {
+  const float sn = FAST ? __sinf(u * a) : sinf(u * a);
+  return fmaf(sn * sn, invb, u);
+}
+
+// u at up-sampled index m (0 <= m < 2T) from the clamped input window xw[i] = x[clamp(n0-5+i)]
+// (static indices only).  q = m - (2*n0 - 5) is the local index.
+template <int Q>
+__device__ __forceinline__ float upsample_at(const float (&xw)[ACT_TT + 10], const float (&fu)[12]) {
+  // m = 2*n0 - 5 + Q.  m odd <=> Q even.  j = floor(m/2) = n0 - 3 + (Q+1)/2 (Q even: m = 2j+1)
+  float acc = 0.f;
+  if ((Q & 1) == 0) {
+    // odd m = 2j+1, j = n0 - 3 + Q/2: taps x[j-2+i] -> window index (j-2+i) - (n0-5) = Q/2 + i
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc = fmaf(xw[Q / 2 + i], fu[10 - 2 * i], acc);
+  } else {
+    // even m = 2j, j = n0 - 3 + (Q+1)/2: taps x[j-3+i] -> window index (Q+1)/2 - 1 + i
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc = fmaf(xw[(Q + 1) / 2 - 1 + i], fu[11 - 2 * i], acc);
+  }
+  return 2.0f * acc;
+}
+
+template <bool FAST, int Q>
+struct SFill {
+  __device__ static __forceinline__ void run(const float (&xw0)[ACT_TT + 10], const float (&xw1)[ACT_TT + 10],
+                                             const float (&fu)[12], float a0, float a1, float ib0, float ib1, int mbase,
+                                             int twoT, float sf0, float sf1, float sl0, float sl1,
+                                             float (&s0)[2 * ACT_TT + 10], float (&s1)[2 * ACT_TT + 10]) {
+    const int m = mbase + Q;
+    float v0 = snake<FAST>(upsample_at<Q>(xw0, fu), a0, ib0);
+    float v1 = snake<FAST>(upsample_at<Q>(xw1, fu), a1, ib1);
+    if (m < 0) { v0 = sf0; v1 = sf1; }
+    if (m > twoT - 1) { v0 = sl0; v1 = sl1; }
+    s0[Q] = v0; s1[Q] = v1;
+    SFill<FAST, Q + 1>::run(xw0, xw1, fu, a0, a1, ib0, ib1, mbase, twoT, sf0, sf1, sl0, sl1, s0, s1);
+  }
+};
+template <bool FAST>
+struct SFill<FAST, 2 * ACT_TT + 10> {
+  __device__ static __forceinline__ void run(const float (&)[ACT_TT + 10], const float (&)[ACT_TT + 10],
+                                             const float (&)[12], float, float, float, float, int, int, float, float,
+                                             float, float, float (&)[2 * ACT_TT + 10], float (&)[2 * ACT_TT + 10]) {}
+};
+
+// blockDim = (bx channel pairs, by time runs); grid = (C/2/bx, ceil(T/(by*ACT_TT)), B)
+template <typename T, bool FAST>
+__global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int n0 = (blockIdx.y * blockDim.y + threadIdx.y) * ACT_TT;
+  const int b = blockIdx.z;
+  if (c >= p.C || n0 >= p.T) return;
+  const int Tm1 = p.T - 1;
+  const T* xb = static_cast<const T*>(p.x) + (int64_t)b * p.T * p.C + c;
+  float fu[12], fd[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { fu[k] = p.fu[k]; fd[k] = p.fd[k]; }
+  const float2 av = *reinterpret_cast<const float2*>(p.a + c);
+  const float2 ib = *reinterpret_cast<const float2*>(p.invb + c);
+  float xw0[ACT_TT + 10], xw1[ACT_TT + 10];
+#pragma unroll
+  for (int i = 0; i < ACT_TT + 10; ++i) {
+    const int t = min(max(n0 - 5 + i, 0), Tm1);
+    ldpair<T>(xb + (int64_t)t * p.C, xw0[i], xw1[i]);
+  }
+  // replicate padding of the activated up-sampled signal: s[-k] = s[0], s[2T-1+k] = s[2T-1]
+  const int mbase = 2 * n0 - 5;
+  const int twoT = 2 * p.T;
+  float sf0 = 0.f, sf1 = 0.f, sl0 = 0.f, sl1 = 0.f;
+  if (mbase < 0) {  // s[0] = snake(u[0]), u[0] = 2*sum x[clamp(-3+i)] fu[11-2i]
+    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float e0, e1;
+      ldpair<T>(xb + (int64_t)min(max(i - 3, 0), Tm1) * p.C, e0, e1);
+      u0 = fmaf(e0, fu[11 - 2 * i], u0); u1 = fmaf(e1, fu[11 - 2 * i], u1);
+    }
+    sf0 = snake<FAST>(2.0f * u0, av.x, ib.x); sf1 = snake<FAST>(2.0f * u1, av.y, ib.y);
+  }
+  if (mbase + 2 * ACT_TT + 9 > twoT - 1) {  // s[2T-1] = snake(u[2(T-1)+1])
+    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float e0, e1;
+      ldpair<T>(xb + (int64_t)min(max(Tm1 - 2 + i, 0), Tm1) * p.C, e0, e1);
+      u0 = fmaf(e0, fu[10 - 2 * i], u0); u1 = fmaf(e1, fu[10 - 2 * i], u1);
+    }
+    sl0 = snake<FAST>(2.0f * u0, av.x, ib.x); sl1 = snake<FAST>(2.0f * u1, av.y, ib.y);
+  }
+  float s0[2 * ACT_TT + 10], s1[2 * ACT_TT + 10];
+  SFill<FAST, 0>::run(xw0, xw1, fu, av.x, av.y, ib.x, ib.y, mbase, twoT, sf0, sf1, sl0, sl1, s0, s1);
+  T* yb = static_cast<T*>(p.y) + (int64_t)b * p.T * p.C + c;
+#pragma unroll
+  for (int j = 0; j < ACT_TT; ++j) {
+    if (n0 + j < p.T) {
+      float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        y0 = fmaf(s0[2 * j + k], fd[k], y0);
+        y1 = fmaf(s1[2 * j + k], fd[k], y1);
+      }
+      stpair<T>(yb + (int64_t)(n0 + j) * p.C, y0, y1);
+    }
+  }
+}
+
+// thread per output sample: tanh(sum_tap sum_c x[t+tap-3,c] w[tap][c] + bias); C % 8 == 0, C <= 128
+template <typename T>
+__global__ void __launch_bounds__(256) conv_out_tanh_kernel(const T* x, const float* w, float bias, int T_, int C,
+                                                            float* wav) {
+  __shared__ float ws[7 * 128];
+  for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_) return;
+  const T* xb = x + (int64_t)b * T_ * C;
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 7; ++tap) {
+    const int tt = t + tap - 3;
+    if (tt < 0 || tt >= T_) continue;
+    const T* row = xb + (int64_t)tt * C;
+    for (int c = 0; c < C; c += 4) {
+      float v[4];
+      ld4<T>(row + c, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc = fmaf(v[j], ws[tap * C + c + j], acc);
+    }
+  }
+  wav[(int64_t)b * T_ + t] = tanhf(acc + bias);
+}
+
+// y[b,t,c] = sum_tap w[tap][c] * wav[b,t+tap-3] + bias[c]
+__global__ void conv_in_wav_kernel(const float* wav, const float* w, const float* bias, int64_t T_, int C, float* y) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (idx >= T_ * C) return;
+  const int c = (int)(idx % C);
+  const int64_t t = idx / C;
+  const float* wb = wav + (int64_t)b * T_;
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 7; ++tap) {
+    const int64_t tt = t + tap - 3;
+    if (tt >= 0 && tt < T_) acc = fmaf(wb[tt], w[tap * C + c], acc);
+  }
+  y[((int64_t)b * T_ + t) * C + c] = acc + bias[c];
+}
+
+__global__ void transpose_out_kernel(const float* x, int T_, int C, float* y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xb = x + (int64_t)b * T_ * C;
+  float* yb = y + (int64_t)b * T_ * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T_ && c < C) tile[i][threadIdx.x] = xb[(int64_t)t * C + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T_ && c < C) yb[(int64_t)c * T_ + t] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+void launch_act1d(const Act1d& p, cudaStream_t stream) {
+  FLM_REQUIRE(p.C % 2 == 0, "act1d: C must be even");
+  if (p.B == 0 || p.T == 0) return;
+  int bx = p.C / 2;
+  if (bx > 128) bx = 128;
+  while ((p.C / 2) % bx) --bx;
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  dim3 block(bx, by);
+  dim3 grid((p.C / 2) / bx, (p.T + by * ACT_TT - 1) / (by * ACT_TT), p.B);
+  FLM_REQUIRE(grid.y <= 65535, "act1d: sequence too long");
+  if (p.io_bf16) {
+    if (p.fast_sin) act1d_kernel<bf16, true><<<grid, block, 0, stream>>>(p);
+    else act1d_kernel<bf16, false><<<grid, block, 0, stream>>>(p);
+  } else {
+    if (p.fast_sin) act1d_kernel<float, true><<<grid, block, 0, stream>>>(p);
+    else act1d_kernel<float, false><<<grid, block, 0, stream>>>(p);
+  }
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_conv_out_tanh(const void* x, int x_bf16, const float* w, float bias, int B, int T, int C, float* wav,
+                          cudaStream_t stream) {
+  FLM_REQUIRE(C % 4 == 0 && C <= 128, "conv_out_tanh: C must be a multiple of 4, <= 128");
+  if (B == 0 || T == 0) return;
+  dim3 grid((T + 255) / 256, B);
+  if (x_bf16)
+    conv_out_tanh_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), w, bias, T, C, wav);
+  else
+    conv_out_tanh_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), w, bias, T, C, wav);
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_conv_in_wav(const float* wav, const float* w, const float* bias, int B, int64_t T, int C, float* y,
+                        cudaStream_t stream) {
+  if (B == 0 || T == 0) return;
+  dim3 grid((unsigned)((T * C + 255) / 256), B);
+  conv_in_wav_kernel<<<grid, 256, 0, stream>>>(wav, w, bias, T, C, y);
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_transpose_out(const float* x, int B, int T, int C, float* y, cudaStream_t stream) {
+  if (B == 0 || T == 0) return;
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  transpose_out_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, T, C, y);
+  FLM_LAUNCH_CHECK();
+}
+
+}  // namespace flm

@@ -1,0 +1,253 @@
+"""Torch-facing wrappers around the C ABI handles.
+
+PyTorch is used here only for device memory, streams and dtype plumbing: every tensor
+that reaches the library is a raw device pointer, every result is written by the
+library's kernels into a torch-allocated output.  One Context per device.
+"""
+import ctypes
+import threading
+from ctypes import byref, c_int64, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import FLM_BF16, FLM_F32, check, flm_prob_cfg, pack_weights
+
+_contexts = {}
+_lock = threading.Lock()
+
+
+def _mode(precision):
+    if precision in ("fp32", "f32", FLM_F32):
+        return FLM_F32
+    if precision in ("bf16", FLM_BF16):
+        return FLM_BF16
+    raise ValueError("precision must be 'fp32' or 'bf16', got %r" % (precision,))
+
+
+class Context:
+    def __init__(self, device):
+        self.lib = _lib.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("flamed_b200 runs on CUDA devices only (no CPU fallback); got %s" % (device,))
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.handle = c_void_p()
+        check(self.lib.flm_ctx_create(idx, byref(self.handle)))
+
+    @staticmethod
+    def get(device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("flamed_b200 runs on CUDA devices only (no CPU fallback); got %s" % (device,))
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        with _lock:
+            if idx not in _contexts:
+                _contexts[idx] = Context(torch.device("cuda", idx))
+            return _contexts[idx]
+
+    def stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+
+def _f32(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p()
+
+
+def _strip(sd, prefix):
+    return [(k[len(prefix):], v) for k, v in sd.items() if k.startswith(prefix)]
+
+
+class DurationEngine:
+    """PVA.sample loop + rounding (pva.py:88-112) and the length regulator (pva.py:125-166)."""
+
+    def __init__(self, ctx, pva_state_dict):
+        self.ctx, self.lib = ctx, ctx.lib
+        named = [(k, v) for k, v in pva_state_dict.items()
+                 if k.startswith("duration_generator.") or k.startswith("sil_generator.")]
+        arr, n, keep = pack_weights(named)
+        self.handle = c_void_p()
+        check(self.lib.flm_durgen_load(ctx.handle, arr, n, byref(self.handle)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.flm_durgen_destroy(self.handle)
+            self.handle = None
+
+    def sample(self, enc, src_mask, noise_dur, noise_sil, ts, temperature):
+        dev = self.ctx.device
+        enc = _f32(enc, dev)
+        B, P, _ = enc.shape
+        noise_dur, noise_sil = _f32(noise_dur, dev), _f32(noise_sil, dev)
+        mask = src_mask.to(device=dev, dtype=torch.uint8).contiguous()
+        ts = ts.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        nfe = ts.numel() - 1
+        phone = torch.empty((B, P), device=dev, dtype=torch.float32)
+        sil = torch.empty_like(phone)
+        dur_t = torch.empty_like(phone)
+        sil_t = torch.empty_like(phone)
+        check(self.lib.flm_durgen_sample(self.handle, _ptr(enc), _ptr(noise_dur), _ptr(noise_sil), _ptr(mask),
+                                         c_void_p(ts.data_ptr()), nfe, float(temperature), B, P, _ptr(phone),
+                                         _ptr(sil), _ptr(dur_t), _ptr(sil_t), self.ctx.stream()))
+        return phone, sil, dur_t, sil_t
+
+    def length_regulate(self, x, phone_dur, sil_dur, src_lens, return_index=False):
+        dev = self.ctx.device
+        x = _f32(x, dev)
+        B, P, H = x.shape
+        phone_dur, sil_dur = _f32(phone_dur, dev), _f32(sil_dur, dev)
+        src_lens = src_lens.to(device=dev, dtype=torch.int64).contiguous()
+        cumsum = torch.empty((B, 2 * P), device=dev, dtype=torch.int32)
+        tgt_len = torch.empty((B,), device=dev, dtype=torch.int64)
+        tmax = c_int64(0)
+        check(self.lib.flm_lr_plan(self.ctx.handle, _ptr(phone_dur), _ptr(sil_dur), _ptr(src_lens), B, P,
+                                   _ptr(cumsum), _ptr(tgt_len), byref(tmax), self.ctx.stream()))
+        T = int(tmax.value)
+        out = torch.empty((B, T, H), device=dev, dtype=torch.float32)
+        index = torch.empty((B, T), device=dev, dtype=torch.int32) if return_index else None
+        check(self.lib.flm_lr_expand(self.ctx.handle, _ptr(x), _ptr(cumsum), B, P, H, T, _ptr(out), _ptr(index),
+                                     self.ctx.stream()))
+        if return_index:
+            return out, tgt_len, index
+        return out, tgt_len
+
+
+class DenoiserEngine:
+    """ProbGenerator.sample (prob_generator.py:434-446) behind flm_cond_prepare / flm_denoiser_sample."""
+
+    def __init__(self, ctx, prob_state_dict, cfg, precision="bf16"):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.precision = precision
+        c = flm_prob_cfg()
+        c.target_dim, c.spk_dim, c.cond_dim = int(cfg["target_dim"]), int(cfg["spk_dim"]), int(cfg["cond_dim"])
+        c.hidden_dim, c.n_layers, c.n_quantizers = int(cfg["hidden_dim"]), int(cfg["n_layers"]), int(cfg["n_quantizers"])
+        c.kernel_size = int(cfg["convnext"]["kernel_size"])
+        c.downsampling_stages = int(cfg["downsampling_stages"])
+        if cfg["convnext"].get("groups") is not None or int(cfg["convnext"].get("expand", 1)) != 1 \
+                or int(cfg["convnext"].get("stride", 1)) != 1:
+            raise RuntimeError("only depthwise ConvNeXt (groups: null, expand 1, stride 1) is implemented")
+        self.cfg = c
+        arr, n, keep = pack_weights(list(prob_state_dict.items()))
+        self.handle = c_void_p()
+        check(self.lib.flm_denoiser_load(ctx.handle, arr, n, byref(c), _mode(precision), byref(self.handle)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.flm_denoiser_destroy(self.handle)
+            self.handle = None
+
+    @property
+    def launches_per_step(self):
+        return int(self.lib.flm_denoiser_launches_per_step(self.handle))
+
+    def cond_prepare(self, prior_embs, mask):
+        """prior_embs (B,Q,L,cond_dim); mask (B,L[,1]) bool True = valid -> cond (B,L,target_dim) fp32"""
+        dev = self.ctx.device
+        prior_embs = _f32(prior_embs, dev)
+        B, Q, L, _ = prior_embs.shape
+        mask = mask.reshape(B, L).to(device=dev, dtype=torch.uint8).contiguous()
+        out = torch.empty((B, L, self.cfg.target_dim), device=dev, dtype=torch.float32)
+        check(self.lib.flm_cond_prepare(self.handle, _ptr(prior_embs), _ptr(mask), B, L, _ptr(out), self.ctx.stream()))
+        return out
+
+    def sample(self, cond, spk, noise, ts, temperature, use_graph=True):
+        """returns latents channels-last (B,L,D); the reference's (B,D,L) is `.transpose(1,2)` of it"""
+        dev = self.ctx.device
+        cond, spk, noise = _f32(cond, dev), _f32(spk, dev), _f32(noise, dev)
+        B, L, D = cond.shape
+        ts = ts.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        nfe = ts.numel() - 1
+        out = torch.empty((B, L, D), device=dev, dtype=torch.float32)
+        check(self.lib.flm_denoiser_sample(self.handle, _ptr(cond), _ptr(spk), _ptr(noise), c_void_p(ts.data_ptr()), B,
+                                           L, nfe, float(temperature), _ptr(out), 1 if use_graph else 0,
+                                           self.ctx.stream()))
+        return out
+
+    def forward(self, x, t, spk):
+        dev = self.ctx.device
+        x, spk = _f32(x, dev), _f32(spk, dev)
+        B, L, D = x.shape
+        out = torch.empty_like(x)
+        check(self.lib.flm_denoiser_forward(self.handle, _ptr(x), _ptr(spk), float(t), B, L, _ptr(out),
+                                            self.ctx.stream()))
+        return out
+
+
+class CodecDecoderEngine:
+    """FACodecDecoder.inference (facodec.py:630-638)."""
+
+    def __init__(self, ctx, state_dict, precision="bf16"):
+        self.ctx, self.lib = ctx, ctx.lib
+        named = [(k, v) for k, v in state_dict.items() if k.startswith("model.") or k.startswith("timbre_linear.")]
+        arr, n, keep = pack_weights(named)
+        self.handle = c_void_p()
+        check(self.lib.flm_codec_dec_load(ctx.handle, arr, n, _mode(precision), byref(self.handle)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.flm_codec_dec_destroy(self.handle)
+            self.handle = None
+
+    def decode(self, latents_bld, spk):
+        """latents (B,L,256) channels-last, spk (B,256) -> wav (B,1,200L)"""
+        dev = self.ctx.device
+        latents_bld, spk = _f32(latents_bld, dev), _f32(spk, dev)
+        B, L, _ = latents_bld.shape
+        hop = 200
+        wav = torch.empty((B, 1, L * hop), device=dev, dtype=torch.float32)
+        check(self.lib.flm_codec_decode(self.handle, _ptr(latents_bld), _ptr(spk), B, L, _ptr(wav), self.ctx.stream()))
+        return wav
+
+    def activation(self, prefix, x_btc):
+        dev = self.ctx.device
+        x_btc = _f32(x_btc, dev)
+        B, T, C = x_btc.shape
+        y = torch.empty_like(x_btc)
+        check(self.lib.flm_codec_dec_activation(self.handle, prefix.encode(), _ptr(x_btc), B, T, C, _ptr(y),
+                                                self.ctx.stream()))
+        return y
+
+
+class CodecEncoderEngine:
+    """FACodecEncoder.forward (facodec.py:215-217)."""
+
+    def __init__(self, ctx, state_dict):
+        self.ctx, self.lib = ctx, ctx.lib
+        arr, n, keep = pack_weights(list(state_dict.items()))
+        self.handle = c_void_p()
+        check(self.lib.flm_codec_enc_load(ctx.handle, arr, n, byref(self.handle)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.flm_codec_enc_destroy(self.handle)
+            self.handle = None
+
+    def encode(self, wav):
+        """wav (B,1,S) -> (B,256,T') in the reference layout"""
+        dev = self.ctx.device
+        wav = _f32(wav, dev)
+        B, _, S = wav.shape
+        T = int(self.lib.flm_codec_enc_frames(self.handle, S))
+        if T <= 0:
+            raise ValueError("prompt of %d samples is too short for the FaCodec encoder" % S)
+        out = torch.empty((B, 256, T), device=dev, dtype=torch.float32)
+        check(self.lib.flm_codec_encode(self.handle, _ptr(wav), B, S, _ptr(out), self.ctx.stream()))
+        return out
+
+
+def tapgemm(ctx, precision, A, W, bias, T_out, ntaps, off0, dil, stride, epi):
+    """test hook: A (B,T_in,K), W (ntaps,N,K), bias (N) or None -> (B,T_out,N)"""
+    dev = ctx.device
+    A, W = _f32(A, dev), _f32(W, dev)
+    bias = _f32(bias, dev) if bias is not None else None
+    B, T_in, K = A.shape
+    N = W.shape[1]
+    out = torch.empty((B, T_out, N), device=dev, dtype=torch.float32)
+    check(ctx.lib.flm_tapgemm_test(ctx.handle, _mode(precision), _ptr(A), _ptr(W), _ptr(bias), B, T_in, T_out, K, N,
+                                   ntaps, off0, dil, stride, epi, _ptr(out), ctx.stream()))
+    return out

@@ -1,0 +1,154 @@
+/*
+ * flamed_b200.h - C ABI of the B200-native Flamed-TTS inference hot path.
+ *
+ * The reference (nghiahuynh-ai/Flamed-TTS) is pure Python/PyTorch and has no FFI of
+ * its own; the boundary a maintainer would bind is the set of Python methods listed
+ * below.  Each entry point replaces the body of one of them ("replaces:" lines cite
+ * /root/reference paths).  The Python side (ctypes stub in INTEGRATION.md, product
+ * binding in flamed_tts_b200/_lib.py) passes raw device pointers of torch tensors and
+ * torch's current CUDA stream.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - every function returns 0 on success, <0 on error; flm_last_error() returns a
+ *     thread-local message.  No exceptions cross the boundary.
+ *   - `*_load` takes HOST fp32 tensors named by the reference's state-dict keys
+ *     (relative to the module), copies and re-packs them into library-owned device
+ *     memory (weight-norm folded, conv taps split, bf16 copies for the tensor-core
+ *     path, adaLN projections concatenated); the caller may free its tensors after.
+ *   - run functions take DEVICE pointers owned by the caller, only enqueue work on
+ *     `stream` and never synchronise, except flm_lr_plan (one documented sync; the
+ *     reference syncs at the same place, pva.py:158).
+ *   - activations are channels-last: (B, T, C) with C contiguous.
+ *   - a handle is not thread-safe; one handle per (device, stream).  Workspaces and
+ *     CUDA-graph caches belong to the handle, keyed by (B, L, nfe).
+ *   - there is no CPU fallback: every entry point fails with FLM_ERR_CUDA if no
+ *     sm_100 device is present.
+ */
+#ifndef FLAMED_B200_H
+#define FLAMED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLM_OK 0
+#define FLM_ERR_ARG (-1)
+#define FLM_ERR_CUDA (-2)
+#define FLM_ERR_WEIGHT (-3)
+#define FLM_ERR_UNSUPPORTED (-4)
+
+/* arithmetic mode of a module handle */
+#define FLM_F32 0  /* fp32 storage, fp32 FMA everywhere (parity mode)                    */
+#define FLM_BF16 1 /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate/state   */
+
+typedef struct flm_ctx flm_ctx;
+typedef struct flm_durgen flm_durgen;
+typedef struct flm_denoiser flm_denoiser;
+typedef struct flm_codec_dec flm_codec_dec;
+typedef struct flm_codec_enc flm_codec_enc;
+typedef void* flm_stream; /* cudaStream_t */
+
+typedef struct {
+  const char* name;  /* reference state-dict key, relative to the module            */
+  const float* data; /* HOST pointer, fp32, contiguous                              */
+  int32_t ndim;
+  int64_t shape[4];
+} flm_tensor;
+
+const char* flm_last_error(void);
+int flm_version(void);
+
+int flm_ctx_create(int device, flm_ctx** out);
+void flm_ctx_destroy(flm_ctx* ctx);
+
+/* ---------------------------------------------------------------- duration / silence generators
+ * replaces: PVA.sample loop + rounding, flamed/models/synthesizer/pva.py:88-112
+ *           (ProbabilisticModule.forward pva.py:221-238, TimeEmbedding pva.py:9-41).
+ * weights: keys relative to `prior_generator.pva.` ("duration_generator.proj.weight", ...).
+ * Always fp32 FMA (durations must round identically to the reference). */
+int flm_durgen_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_durgen** out);
+void flm_durgen_destroy(flm_durgen* h);
+/* enc (B,P,192) f32; noise_* (B,P) f32 standard normal (dur first, pva.py:101-102);
+ * src_mask (B,P) u8, 1 = padding; ts (nfe+1) f32 HOST = torch.linspace(0,1,nfe+1);
+ * out_phone/out_sil (B,P) f32 holding clamp(round(exp(x)-1),0); out_dur_t/out_sil_t (B,P) f32
+ * = the ODE state before rounding (may be NULL). */
+int flm_durgen_sample(flm_durgen* h, const float* enc, const float* noise_dur, const float* noise_sil,
+                      const uint8_t* src_mask, const float* ts_host, int nfe, float temperature, int B, int P,
+                      float* out_phone, float* out_sil, float* out_dur_t, float* out_sil_t, flm_stream stream);
+
+/* ---------------------------------------------------------------- length regulator
+ * replaces: LengthRegulator.LR, pva.py:125-166 (+ pad, flamed/utils/tools.py:299-317).
+ * plan: integer repeats -> inclusive cumsum (B,2P) i32 + tgt_len (B) i64 on device, and the
+ * batch maximum on the host (one stream sync, as pva.py:158 `.tolist()`). */
+int flm_lr_plan(flm_ctx* ctx, const float* phone_dur, const float* sil_dur, const int64_t* src_lens, int B, int P,
+                int32_t* out_cumsum, int64_t* out_tgt_len, int64_t* out_tmax_host, flm_stream stream);
+/* expand: out (B,Tmax,H) f32 = gather of x (B,P,H) f32, zero beyond tgt_len;
+ * out_index (B,Tmax) i32 = source phoneme row, -1 for padding (may be NULL). */
+int flm_lr_expand(flm_ctx* ctx, const float* x, const int32_t* cumsum, int B, int P, int H, int Tmax, float* out,
+                  int32_t* out_index, flm_stream stream);
+
+/* ---------------------------------------------------------------- code-decoder denoiser
+ * replaces: ProbGenerator.sample, flamed/models/synthesizer/prob_generator.py:434-446
+ *           (QuantizerEncoding 375-381, ConditionDownSampler 198-205, SimpleMLPAdaLN 349-365).
+ * weights: keys relative to `prob_generator.`; cfg taken from configs/prob.yaml. */
+typedef struct {
+  int32_t target_dim, spk_dim, cond_dim, hidden_dim, n_layers, n_quantizers, kernel_size, downsampling_stages;
+} flm_prob_cfg;
+int flm_denoiser_load(flm_ctx* ctx, const flm_tensor* weights, int n, const flm_prob_cfg* cfg, int mode,
+                      flm_denoiser** out);
+void flm_denoiser_destroy(flm_denoiser* h);
+/* prior_embs (B,Q,L,cond_dim) f32; mask (B,L) u8, 1 = valid frame; out_cond (B,L,target_dim) f32 */
+int flm_cond_prepare(flm_denoiser* h, const float* prior_embs, const uint8_t* mask, int B, int L, float* out_cond,
+                     flm_stream stream);
+/* cond (B,L,D) f32; spk (B,spk_dim) f32; noise (B,L,D) f32 standard normal (prob_generator.py:440);
+ * ts (nfe+1) f32 HOST; out_latents (B,L,D) f32 channels-last: the reference returns its
+ * transpose(1,2) VIEW (prob_generator.py:446).  The whole nfe-step loop runs as one CUDA graph
+ * (use_graph != 0), cached per (B,L,nfe). */
+int flm_denoiser_sample(flm_denoiser* h, const float* cond, const float* spk, const float* noise, const float* ts_host,
+                        int B, int L, int nfe, float temperature, float* out_latents, int use_graph,
+                        flm_stream stream);
+/* one velocity evaluation v = denoiser(x, t, spk) (SimpleMLPAdaLN.forward), for parity tests */
+int flm_denoiser_forward(flm_denoiser* h, const float* x, const float* spk, float t, int B, int L, float* out_v,
+                         flm_stream stream);
+/* number of kernels launched per Euler step (for bench.py's gpu_launches) */
+int flm_denoiser_launches_per_step(flm_denoiser* h);
+
+/* ---------------------------------------------------------------- FaCodec decoder
+ * replaces: FACodecDecoder.inference, flamed/models/facodec/facodec.py:630-638 (model stack
+ *           400-415, DecoderBlock 246-265, ResidualUnit 121-133, Activation1d act.py:24-29).
+ * weights: keys of FACodecDecoder.state_dict() (`model.*`, `timbre_linear.*`; others ignored). */
+int flm_codec_dec_load(flm_ctx* ctx, const flm_tensor* weights, int n, int mode, flm_codec_dec** out);
+void flm_codec_dec_destroy(flm_codec_dec* h);
+/* latents (B,L,256) f32 channels-last; spk (B,256) f32; out_wav (B,1,200*L) f32 */
+int flm_codec_decode(flm_codec_dec* h, const float* latents, const float* spk, int B, int L, float* out_wav,
+                     flm_stream stream);
+/* one anti-aliased Snake activation (Activation1d) of the decoder, by state-dict prefix
+ * (e.g. "model.5"); x,y (B,T,C) f32 channels-last.  For parity tests. */
+int flm_codec_dec_activation(flm_codec_dec* h, const char* prefix, const float* x, int B, int T, int C, float* y,
+                             flm_stream stream);
+
+/* ---------------------------------------------------------------- FaCodec encoder (prompt)
+ * replaces: FACodecEncoder.forward, facodec.py:215-217 (ctor 183-213, EncoderBlock 136-155). */
+int flm_codec_enc_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_codec_enc** out);
+void flm_codec_enc_destroy(flm_codec_enc* h);
+/* returns the number of output frames for S input samples (<=0: too short) */
+int64_t flm_codec_enc_frames(flm_codec_enc* h, int64_t S);
+/* wav (B,1,S) f32; out (B,256,T') f32 in the REFERENCE layout (channels-first) */
+int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S, float* out, flm_stream stream);
+
+/* ---------------------------------------------------------------- generic kernels exposed for tests
+ * out[b,t,n] = epi(sum_tap sum_k A[b, t*stride + off0 + tap*dil, k] * W[tap][n][k] + bias[n]),
+ * rows outside [0,T_in) read as zero.  A (B,T_in,K) f32, W (ntaps,N,K) f32, out (B,T_out,N) f32.
+ * mode FLM_F32 runs the fp32 FMA kernel, FLM_BF16 converts operands to bf16 and runs the
+ * tcgen05/TMA kernel (stride must be 1).  epi: 0 none, 1 gelu(erf), 2 silu, 3 relu. */
+int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, const float* bias, int B, int T_in,
+                     int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi, float* out,
+                     flm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLAMED_B200_H */
