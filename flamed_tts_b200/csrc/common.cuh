@@ -19,9 +19,11 @@ struct Error : std::runtime_error {
 #define FLM_CUDA(expr)                                                                              \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess)                                                                          \
+    if (_e != cudaSuccess) {                                                                        \
+      cudaGetLastError(); /* clear the sticky last-error so later launch checks are not poisoned */  \
       throw flm::Error(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
                                std::to_string(__LINE__) + ")");                                     \
+    }                                                                                               \
   } while (0)
 
 #define FLM_REQUIRE(cond, msg)                                                  \

@@ -188,10 +188,16 @@ struct Engine {
   }
 };
 
-// CUDA-graph cache: body(stream) is captured once per key and replayed afterwards
+// CUDA-graph cache: body(stream) is captured once per key on a private stream (capture is not
+// allowed on the legacy default stream, which is what torch hands us by default) and the
+// instantiated graph is then launched on the caller's stream.
 struct GraphCache {
   std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> execs;
-  ~GraphCache() { clear(); }
+  cudaStream_t capture_stream = nullptr;
+  ~GraphCache() {
+    clear();
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
   void clear() {
     for (auto& kv : execs) cudaGraphExecDestroy(kv.second);
     execs.clear();
@@ -199,16 +205,18 @@ struct GraphCache {
   void run(std::tuple<int, int, int, int> key, cudaStream_t stream, const std::function<void(cudaStream_t)>& body) {
     auto it = execs.find(key);
     if (it == execs.end()) {
+      if (!capture_stream) FLM_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
-      FLM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+      FLM_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeRelaxed));
       try {
-        body(stream);
+        body(capture_stream);
       } catch (...) {
-        cudaStreamEndCapture(stream, &graph);
+        cudaStreamEndCapture(capture_stream, &graph);
         if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
         throw;
       }
-      FLM_CUDA(cudaStreamEndCapture(stream, &graph));
+      FLM_CUDA(cudaStreamEndCapture(capture_stream, &graph));
       cudaGraphExec_t exec = nullptr;
       cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
