@@ -87,7 +87,10 @@ class ProbGenerator(EngineOwner):
         self.denoiser = SimpleMLPAdaLN(config["target_dim"], config["hidden_dim"], config["target_dim"],
                                        config["spk_dim"], config["n_layers"], config["convnext"]["kernel_size"])
         self.noise_device = "cpu"
-        self.use_cuda_graph = True
+        # True / False / "auto": one CUDA graph per (B, L, nfe) pays off when the kernels are short
+        # (launch-bound, few frames); big batches are launched directly (kernels of ~100 us hide the launches)
+        self.use_cuda_graph = "auto"
+        self.graph_max_rows = 16384
 
     def _build_engine(self, ctx):
         from flamed_tts_b200.engines import DenoiserEngine
@@ -107,5 +110,6 @@ class ProbGenerator(EngineOwner):
         ts = torch.linspace(0, 1, nfe + 1)
         ndev = c.device if self.noise_device == "cuda" else "cpu"
         noise = torch.randn((b, l, self.target_dim), device=ndev)
-        x = eng.sample(c, spk, noise, ts, temperature, use_graph=self.use_cuda_graph)
+        graph = (b * l <= self.graph_max_rows) if self.use_cuda_graph == "auto" else bool(self.use_cuda_graph)
+        x = eng.sample(c, spk, noise, ts, temperature, use_graph=graph)
         return x.transpose(1, -1)

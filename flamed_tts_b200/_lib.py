@@ -27,6 +27,7 @@ class flm_prob_cfg(ctypes.Structure):
 SIGNATURES = {
     "flm_last_error": (c_char_p, []),
     "flm_version": (c_int, []),
+    "flm_launch_count": (ctypes.c_ulonglong, []),
     "flm_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "flm_ctx_destroy": (None, [c_void_p]),
     "flm_durgen_load": (c_int, [c_void_p, POINTER(flm_tensor), c_int, POINTER(c_void_p)]),
@@ -52,8 +53,13 @@ SIGNATURES = {
     "flm_codec_enc_destroy": (None, [c_void_p]),
     "flm_codec_enc_frames": (c_int64, [c_void_p, c_int64]),
     "flm_codec_encode": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "flm_profile_enable": (c_int, [c_void_p, c_int]),
+    "flm_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), c_int]),
+    "flm_profile_class_name": (c_char_p, [c_int]),
     "flm_tapgemm_test": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "flm_tapgemm_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  POINTER(c_float), c_void_p]),
 }
 
 _lib = None

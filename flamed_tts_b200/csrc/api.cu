@@ -8,6 +8,7 @@
 using namespace flm;
 
 static thread_local std::string g_last_error;
+namespace flm { unsigned long long g_launch_count = 0; }
 
 #define FLM_API_BEGIN try {
 #define FLM_API_END                          \
@@ -24,6 +25,7 @@ static thread_local std::string g_last_error;
 
 extern "C" const char* flm_last_error(void) { return g_last_error.c_str(); }
 extern "C" int flm_version(void) { return 100; }
+extern "C" unsigned long long flm_launch_count(void) { return flm::g_launch_count; }
 
 // ===================================================================================== context
 extern "C" int flm_ctx_create(int device, flm_ctx** out) {
@@ -343,14 +345,24 @@ struct flm_denoiser : Engine {
     DwConv dw;
     dw.x = bufU.p; dw.y = bufD.p; dw.io_bf16 = b16; dw.w = c.dw_w; dw.bias = c.dw_b; dw.part = part.as<float>();
     dw.B = B; dw.L = L; dw.C = H; dw.KW = cfg.kernel_size;
-    launch_dwconv(dw, s);
-    launch_gn_finalize(part.as<float>(), B, L, H, H, dw_nchunk(L), DW_TT, c.gn_w, c.gn_b, 1e-5f, gsc.as<float>(),
-                       gof.as<float>(), s);
+    const double elems = (double)B * L * H, eb = (double)esize();
+    {
+      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * cfg.kernel_size, elems * 2 * eb);
+      launch_dwconv(dw, s);
+    }
+    {
+      ProfScope ps(ctx, KC_GN_FINALIZE, s, 0, (double)B * dw_nchunk(L) * H * 8);
+      launch_gn_finalize(part.as<float>(), B, L, H, H, dw_nchunk(L), DW_TT, c.gn_w, c.gn_b, 1e-5f, gsc.as<float>(),
+                         gof.as<float>(), s);
+    }
     GnApply ga;
     memset(&ga, 0, sizeof(ga));
     ga.x = bufD.p; ga.x_bf16 = b16; ga.y = bufG.p; ga.y_bf16 = b16; ga.scale = gsc.as<float>();
     ga.offset = gof.as<float>(); ga.B = B; ga.L = L; ga.C = H;
-    launch_gn_apply(ga, s);
+    {
+      ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * eb);
+      launch_gn_apply(ga, s);
+    }
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
     p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
@@ -365,6 +377,7 @@ struct flm_denoiser : Engine {
     ln.x = h.as<float>(); ln.ldx = H; ln.y = y; ln.ldy = H; ln.y_bf16 = bf() ? 1 : 0;
     ln.w = w; ln.b = b; ln.shift = shift; ln.scale = scale; ln.mod_bstride = ada_n; ln.scale_plus_one = 1.f;
     ln.eps = 1e-6f; ln.rows = (int64_t)B * L; ln.rows_per_batch = L; ln.C = H;
+    ProfScope ps(ctx, KC_LN_MOD, s, (double)B * L * H * 8, (double)B * L * H * (4 + esize()));
     launch_ln_mod(ln, s);
   }
 
@@ -600,6 +613,8 @@ void run_act(const Engine& e, const ActW& a, const void* x, void* y, int B, int 
   memcpy(p.fu, a.fu, sizeof(p.fu));
   memcpy(p.fd, a.fd, sizeof(p.fd));
   p.B = B; p.T = T; p.C = a.C; p.fast_sin = e.bf() ? 1 : 0;
+  const double elems = (double)B * T * a.C;
+  ProfScope ps(e.ctx, KC_ACT1D, s, elems * 52, elems * 2 * e.esize());
   launch_act1d(p, s);
 }
 
@@ -654,6 +669,7 @@ extern "C" int flm_codec_dec_load(flm_ctx* ctx, const flm_tensor* weights, int n
     blk.up = h->make_layer(pack_conv_transpose(w, blk.cin, blk.cout, blk.stride),
                            replicate(wm.vec(p + ".block.1.bias", {blk.cout}), blk.stride), blk.cin,
                            blk.stride * blk.cout, 3, -1, 1, 1, b);
+    blk.up.alg_scale = 2.0f / 3.0f;  // each output frame really uses 2 of the 3 zero-padded taps
     const int dils[3] = {1, 3, 9};
     for (int j = 0; j < 3; ++j) {
       const std::string rp = p + ".block." + std::to_string(j + 2);
@@ -842,6 +858,41 @@ extern "C" int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64
   FLM_API_END
 }
 
+// ===================================================================================== profiler
+extern "C" int flm_profile_enable(flm_ctx* ctx, int on) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx != nullptr, "null ctx");
+  set_device(ctx);
+  FLM_CUDA(cudaDeviceSynchronize());
+  for (auto& r : ctx->recs) { ctx->pool.push_back(r.a); ctx->pool.push_back(r.b); }
+  ctx->recs.clear();
+  ctx->prof_on = on != 0;
+  FLM_API_END
+}
+
+extern "C" int flm_profile_read(flm_ctx* ctx, double* out, int n_classes) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && out && n_classes >= KC_COUNT, "bad arguments (need room for 8 classes x 4 doubles)");
+  set_device(ctx);
+  FLM_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes * 4; ++i) out[i] = 0.0;
+  for (auto& r : ctx->recs) {
+    float ms = 0.f;
+    FLM_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    out[r.kc * 4 + 0] += 1.0;
+    out[r.kc * 4 + 1] += ms;
+    out[r.kc * 4 + 2] += r.flops;
+    out[r.kc * 4 + 3] += r.bytes;
+  }
+  FLM_API_END
+}
+
+extern "C" const char* flm_profile_class_name(int kc) {
+  static const char* names[KC_COUNT] = {"tapgemm_tcgen05", "tapgemm_fp32_fma", "ln_modulate", "dwconv31_stats",
+                                        "groupnorm_finalize", "groupnorm_apply", "snake_act1d", "other"};
+  return (kc >= 0 && kc < KC_COUNT) ? names[kc] : "?";
+}
+
 // ===================================================================================== test hook
 extern "C" int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, const float* bias, int B,
                                 int T_in, int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi,
@@ -868,5 +919,50 @@ extern "C" int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const fl
     launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
     FLM_CUDA(cudaStreamSynchronize(s));  // a16/w16 are freed on return
   }
+  FLM_API_END
+}
+
+// ---- micro-benchmark hook: `reps` back-to-back launches of one tap-GEMM on pseudo-random operands,
+// timed with CUDA events on `stream`; *out_ms = average ms per launch.  epi 0..3, or 5 (gated residual).
+// Operands are pseudo-random (zeros would under-state the power draw and over-state the clocks).
+extern "C" int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, int N, int ntaps, int dil, int epi,
+                                 int out_bf16, int reps, float* out_ms, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && out_ms && reps > 0, "bad arguments");
+  set_device(ctx);
+  cudaStream_t s = S(stream);
+  const size_t e = mode == FLM_BF16 ? 2 : 4;
+  const int64_t M = (int64_t)B * T;
+  DevBuf a, w, o, h, g, bias;
+  a.ensure(M * K * e); w.ensure((size_t)ntaps * N * K * e); o.ensure(M * N * 4); h.ensure(M * N * 4);
+  g.ensure((size_t)B * N * 4); bias.ensure((size_t)N * 4);
+  launch_fill_random(a.p, mode == FLM_BF16, M * K, 1u, 1.0f, s);
+  launch_fill_random(w.p, mode == FLM_BF16, (int64_t)ntaps * N * K, 2u, 0.03f, s);
+  launch_fill_random(h.p, 0, M * N, 3u, 1.0f, s);
+  launch_fill_random(g.p, 0, (int64_t)B * N, 4u, 0.1f, s);
+  launch_fill_random(bias.p, 0, N, 5u, 0.1f, s);
+  TapGemm p;
+  memset(&p, 0, sizeof(p));
+  p.A = a.p; p.W = w.p; p.bias = bias.as<float>(); p.out = o.p; p.lda = K; p.ldc = N; p.B = B; p.T_in = T; p.T_out = T;
+  p.K = K; p.N = N; p.ntaps = ntaps; p.off0 = -(ntaps / 2) * dil; p.dil = dil; p.stride = 1; p.epi = epi;
+  p.out_bf16 = out_bf16;
+  p.gate = g.as<float>(); p.gate_bstride = N; p.hres = h.as<float>(); p.ld_res = N;
+  cudaEvent_t e0, e1;
+  FLM_CUDA(cudaEventCreate(&e0));
+  FLM_CUDA(cudaEventCreate(&e1));
+  auto launch = [&]() {
+    if (mode == FLM_BF16) launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
+    else launch_tapgemm_simt(p, s);
+  };
+  for (int i = 0; i < 3; ++i) launch();
+  FLM_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < reps; ++i) launch();
+  FLM_CUDA(cudaEventRecord(e1, s));
+  FLM_CUDA(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  FLM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *out_ms = ms / reps;
   FLM_API_END
 }

@@ -31,7 +31,13 @@ struct Error : std::runtime_error {
     if (!(cond)) throw flm::Error(-1, std::string("argument error: ") + (msg)); \
   } while (0)
 
-#define FLM_LAUNCH_CHECK() FLM_CUDA(cudaGetLastError())
+// every kernel launcher ends with this: checks the launch and counts it (flm_launch_count)
+extern unsigned long long g_launch_count;
+#define FLM_LAUNCH_CHECK()          \
+  do {                              \
+    ++flm::g_launch_count;          \
+    FLM_CUDA(cudaGetLastError());   \
+  } while (0)
 
 // ---- element access in storage type T (float or bf16), arithmetic always fp32
 template <typename T>

@@ -17,13 +17,58 @@
 #include "common.cuh"
 #include "kernels.h"
 
+// kernel classes of the per-launch profiler (flm_profile_*): CUDA events around every launch
+enum KClass : int {
+  KC_GEMM_TC = 0,   // tcgen05 / TMA tap-GEMM
+  KC_GEMM_FMA,      // fp32 FMA tap-GEMM
+  KC_LN_MOD,        // LayerNorm + adaLN modulate
+  KC_DWCONV,        // depthwise k=31 + GroupNorm partial statistics
+  KC_GN_FINALIZE,
+  KC_GN_APPLY,
+  KC_ACT1D,         // anti-aliased Snake activation
+  KC_OTHER,
+  KC_COUNT
+};
+
 struct flm_ctx {
   int device = 0;
   int num_sms = 0;
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled
+  // profiler state
+  bool prof_on = false;
+  struct Rec { int kc; cudaEvent_t a, b; double flops, bytes; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ~flm_ctx() {
+    for (auto& r : recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+  }
 };
 
 namespace flm {
+
+// records a CUDA-event pair around the launches issued during its lifetime (profiling mode only,
+// never while the stream is being captured into a graph)
+struct ProfScope {
+  flm_ctx* c; cudaStream_t s; cudaEvent_t b = nullptr;
+  ProfScope(flm_ctx* ctx, int kc, cudaStream_t st, double flops, double bytes) : c(ctx), s(st) {
+    if (!c->prof_on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    flm_ctx::Rec r;
+    r.kc = kc; r.a = c->get_event(); r.b = c->get_event(); r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.a, s);
+    b = r.b;
+    c->recs.push_back(r);
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, s); }
+};
 
 struct DevBuf {
   void* p = nullptr;
@@ -100,6 +145,7 @@ struct WeightMap {
 // a dense / conv layer in tap-GEMM form
 struct Layer {
   int K = 0, N = 0, ntaps = 1, off0 = 0, dil = 1, stride = 1;
+  float alg_scale = 1.f;  // algorithmic / executed FLOPs (2/3 for the zero-padded transposed-conv taps)
   float* w32 = nullptr;  // (ntaps, N, K)
   bf16* w16 = nullptr;   // same, bf16 (only when the module runs in FLM_BF16)
   float* bias = nullptr; // (N)
@@ -177,6 +223,11 @@ struct Engine {
   }
   // fp32 FMA kernel (A fp32) or tcgen05 kernel (A bf16), chosen by `a_bf16`
   void gemm(TapGemm p, const Layer& l, bool a_bf16, cudaStream_t s) const {
+    const double M = (double)p.B * p.T_out;
+    const double flops = 2.0 * M * p.N * p.K * p.ntaps * l.alg_scale;
+    const double bytes = M * p.K * (a_bf16 ? 2 : 4) + (double)p.ntaps * p.N * p.K * (a_bf16 ? 2 : 4) +
+                         M * p.N * ((p.epi == EPI_GATE_RESID || p.epi == EPI_EULER) ? 8 : (p.out_bf16 ? 2 : 4));
+    ProfScope ps(ctx, a_bf16 ? KC_GEMM_TC : KC_GEMM_FMA, s, flops, bytes);
     if (a_bf16) {
       if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");
       p.W = l.w16;
@@ -193,6 +244,7 @@ struct Engine {
 // instantiated graph is then launched on the caller's stream.
 struct GraphCache {
   std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> execs;
+  std::map<cudaGraphExec_t, unsigned long long> kernels_in;  // kernel nodes per graph (launch accounting)
   cudaStream_t capture_stream = nullptr;
   ~GraphCache() {
     clear();
@@ -201,12 +253,14 @@ struct GraphCache {
   void clear() {
     for (auto& kv : execs) cudaGraphExecDestroy(kv.second);
     execs.clear();
+    kernels_in.clear();
   }
   void run(std::tuple<int, int, int, int> key, cudaStream_t stream, const std::function<void(cudaStream_t)>& body) {
     auto it = execs.find(key);
     if (it == execs.end()) {
       if (!capture_stream) FLM_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
+      const unsigned long long before = g_launch_count;
       FLM_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeRelaxed));
       try {
         body(capture_stream);
@@ -222,7 +276,10 @@ struct GraphCache {
       cudaGraphDestroy(graph);
       FLM_CUDA(e);
       it = execs.emplace(key, exec).first;
+      kernels_in[exec] = g_launch_count - before;
+      g_launch_count = before;  // captured, not launched: counted at each replay below
     }
+    g_launch_count += kernels_in[it->second];
     FLM_CUDA(cudaGraphLaunch(it->second, stream));
   }
 };

@@ -74,6 +74,7 @@ void launch_silu_sum(const float* temb, const float* cvec, int nfe, int B, int C
 // x0 = noise * temperature + cond  (prob_generator.py:440); also writes a bf16 copy if xb != null
 void launch_noise_init(const float* noise, const float* cond, float temperature, int64_t n, float* x, cudaStream_t s);
 void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+void launch_fill_random(void* x, int is_bf16, int64_t n, uint32_t seed, float scale, cudaStream_t stream);
 
 // ---- cond down-sampler front end: xq[b,l,q*D+d] = prior[b,q,l,d] + qemb[q,d]; xm = xq * mask
 void launch_quantizer_fold(const float* prior, const float* qemb, const uint8_t* mask, int B, int Q, int L, int D,

@@ -208,9 +208,26 @@ __global__ void __launch_bounds__(256) lr_expand_kernel(const float* x, const in
   if (out_index && lane == 0) out_index[(int64_t)b * Tmax + f] = src;
 }
 
+// deterministic pseudo-random fill in [-scale, scale] (benchmark operands; zeros would under-state power)
+template <typename T>
+__global__ void fill_random_kernel(T* x, int64_t n, uint32_t seed, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t h = (uint32_t)i * 2654435761u ^ seed;
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  stf<T>(x + i, ((float)(h & 0xFFFF) / 32768.0f - 1.0f) * scale);
+}
+
 inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
+
+void launch_fill_random(void* x, int is_bf16, int64_t n, uint32_t seed, float scale, cudaStream_t stream) {
+  if (n == 0) return;
+  if (is_bf16) fill_random_kernel<bf16><<<nblk(n), 256, 0, stream>>>(static_cast<bf16*>(x), n, seed, scale);
+  else fill_random_kernel<float><<<nblk(n), 256, 0, stream>>>(static_cast<float*>(x), n, seed, scale);
+  FLM_LAUNCH_CHECK();
+}
 
 void launch_timestep_embedding(const float* ts, int n, int dim, float* out, cudaStream_t stream) {
   if (n == 0) return;

@@ -9,8 +9,12 @@
 //   warp 1      MMA issuer    - tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16 per
 //                               instruction, accumulators in TMEM (2 stages x BLOCK_N columns), smem
 //                               slots released with tcgen05.commit
-//   warps 2..5  epilogue      - tcgen05.ld (32 lanes x 32 columns per warp), bias / activation /
-//                               adaLN-gated residual / Euler update fused, direct 64-128 B per-thread stores
+//   warps 2..9  epilogue      - two warps per TMEM lane quarter, each taking every other 32-column chunk:
+//                               tcgen05.ld (32 lanes x 32 columns), bias + activation fused and stored
+//                               straight from registers (64-128 B per thread); the residual epilogues
+//                               (adaLN-gated residual, Euler update, codec skip) transpose the chunk
+//                               through shared memory so that every global load/store is a coalesced
+//                               128 B row segment and all loads of 8 rows are in flight together
 // smem ring: STAGES x (16 KiB A + BLOCK_N*128 B W), SWIZZLE_128B on both sides (TMA writes it, the UMMA
 // shared-memory descriptor reads it).
 //
@@ -29,14 +33,19 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int STAGE_LD = 33;  // padded row of the epilogue transpose buffer (floats)
 
 template <int BLOCK_N>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages; 128/256/512: power of two
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * STAGE_LD * 4;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ +
+                                    EPI_STAGE_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -130,81 +139,100 @@ struct Sched {
   int num_tiles, num_n_tiles, tiles_m_per_b, flatten;
 };
 
-// ---------------------------------------------------------------- epilogue on 32 consecutive columns of one row
-__device__ __forceinline__ void epilogue_row32(const TapGemm& p, float (&v)[32], int64_t m, int b, int n) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// first row / sample / frame / valid-row count of epilogue quarter `quarter` of M tile `mt`
+__device__ __forceinline__ void warp_rows(const TapGemm& p, const Sched& sch, int mt, int quarter, int64_t& m_w, int& b_w,
+                                          int& t_w, int& rows_valid) {
+  if (sch.flatten) {
+    m_w = (int64_t)mt * BLOCK_M + quarter * 32;
+    const int64_t total = (int64_t)p.B * p.T_out;
+    rows_valid = (int)max((int64_t)0, min((int64_t)32, total - m_w));
+    b_w = (int)(m_w / p.T_out);
+    t_w = (int)(m_w % p.T_out);
+  } else {
+    b_w = mt / sch.tiles_m_per_b;
+    t_w = (mt % sch.tiles_m_per_b) * BLOCK_M + quarter * 32;
+    rows_valid = max(0, min(32, p.T_out - t_w));
+    m_w = (int64_t)b_w * p.T_out + t_w;
+  }
+}
+
+// pull the residual-stream / addend segments a warp will read in the epilogue of `tile` into L2 while the
+// tensor core is still busy with it (lane = row, one 128 B line per 32-column chunk)
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void prefetch_epilogue_operands(const TapGemm& p, const Sched& sch, int tile, int quarter,
+                                                           int half, int lane) {
+  const int nt = tile % sch.num_n_tiles, mt = tile / sch.num_n_tiles;
+  int64_t m_w;
+  int b_w, t_w, rows_valid;
+  warp_rows(p, sch, mt, quarter, m_w, b_w, t_w, rows_valid);
+  if (lane >= rows_valid) return;
+  const int64_t m = m_w + lane;
+#pragma unroll
+  for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
+    const int n = nt * BLOCK_N + ch * 32;
+    if (EPI == EPI_RESID) {
+      if (p.out_bf16) prefetch_l2(static_cast<const bf16*>(p.resid_in) + m * p.ldc + n);
+      else prefetch_l2(static_cast<const float*>(p.resid_in) + m * p.ldc + n);
+    } else {
+      prefetch_l2(p.hres + m * p.ld_res + n);
+    }
+    if (EPI == EPI_GATE_RESID && p.addend) {
+      if (p.addend_bf16) prefetch_l2(static_cast<const bf16*>(p.addend) + m * p.ld_add + n);
+      else prefetch_l2(static_cast<const float*>(p.addend) + m * p.ld_add + n);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- epilogues
+// fast forms for the bf16 mode (results are rounded to bf16 or feed a bf16 GEMM): erf by
+// Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7), exp by MUFU.EX2
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = ex2_approx(z * z * -1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float silu_fast(float x) {
+  return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));
+}
+
+template <int EPI>
+__device__ __forceinline__ float act_fast(float v) {
+  if (EPI == EPI_GELU) return gelu_fast(v);
+  if (EPI == EPI_SILU) return silu_fast(v);
+  if (EPI == EPI_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+// (a) activation epilogues: thread = row, 32 consecutive columns from registers
+template <int EPI>
+__device__ __forceinline__ void epilogue_direct(const TapGemm& p, float (&v)[32], int64_t m, int n) {
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(p.bias + n + j);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
       v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
     }
   }
-  if (p.epi == EPI_GATE_RESID || p.epi == EPI_EULER) {
-    float* h = p.hres + m * p.ld_res + n;
-    if (p.epi == EPI_GATE_RESID) {
-      if (p.addend) {
-        if (p.addend_bf16) {
-          const bf16* a = static_cast<const bf16*>(p.addend) + m * p.ld_add + n;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float t[4];
-            ld4<bf16>(a + j, t);
-            v[j] += t[0]; v[j + 1] += t[1]; v[j + 2] += t[2]; v[j + 3] += t[3];
-          }
-        } else {
-          const float* a = static_cast<const float*>(p.addend) + m * p.ld_add + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float t[4];
-            ld4<float>(a + j, t);
-            v[j] += t[0]; v[j + 1] += t[1]; v[j + 2] += t[2]; v[j + 3] += t[3];
-          }
-        }
-      }
-      const float* g = p.gate + (int64_t)b * p.gate_bstride + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float hv[4], gv[4];
-        ld4<float>(h + j, hv);
-        ld4<float>(g + j, gv);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hv[q] = __fadd_rn(hv[q], __fmul_rn(gv[q], v[j + q]));
-        st4<float>(h + j, hv);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float hv[4];
-        ld4<float>(h + j, hv);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hv[q] = __fadd_rn(hv[q], __fmul_rn(p.alpha, v[j + q]));
-        st4<float>(h + j, hv);
-      }
-    }
-    return;
-  }
-  if (p.epi == EPI_RESID) {
-    if (p.out_bf16) {
-      const bf16* r = static_cast<const bf16*>(p.resid_in) + m * p.ldc + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float t[4];
-        ld4<bf16>(r + j, t);
-        v[j] += t[0]; v[j + 1] += t[1]; v[j + 2] += t[2]; v[j + 3] += t[3];
-      }
-    } else {
-      const float* r = static_cast<const float*>(p.resid_in) + m * p.ldc + n;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float t[4];
-        ld4<float>(r + j, t);
-        v[j] += t[0]; v[j + 1] += t[1]; v[j + 2] += t[2]; v[j + 3] += t[3];
-      }
-    }
-  } else if (p.epi != EPI_NONE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = epi_act(p.epi, v[j]);
-  }
+  for (int j = 0; j < 32; ++j) v[j] = act_fast<EPI>(v[j]);
   if (p.out_bf16) {
     bf16* o = static_cast<bf16*>(p.out) + m * p.ldc + n;
 #pragma unroll
@@ -225,8 +253,84 @@ __device__ __forceinline__ void epilogue_row32(const TapGemm& p, float (&v)[32],
   }
 }
 
+// (b) residual epilogues: the warp's 32x32 chunk is transposed through `stage` (32 x STAGE_LD floats) so
+// that lane = column: every global access of a row is one coalesced 128 B (fp32) / 64 B (bf16) segment.
+// All loads of the chunk are issued before the first use.  FULL: all 32 rows valid and in one sample (the
+// common case, no predicates, running pointers); otherwise the valid rows are a prefix of length rows_valid.
+template <int EPI, bool FULL, typename TRES, typename TADD>
+__device__ __forceinline__ void epilogue_rows(const TapGemm& p, const float* stage, int lane, int64_t m_base,
+                                              int rows_valid, int b0, int t0, int col, float bias) {
+  // residual source / destination for this lane's column
+  const TRES* rsrc;
+  TRES* rdst;
+  int64_t rld;
+  if (EPI == EPI_RESID) {
+    rsrc = static_cast<const TRES*>(p.resid_in) + m_base * p.ldc + col;
+    rdst = static_cast<TRES*>(p.out) + m_base * p.ldc + col;
+    rld = p.ldc;
+  } else {
+    rsrc = reinterpret_cast<const TRES*>(p.hres) + m_base * p.ld_res + col;
+    rdst = reinterpret_cast<TRES*>(p.hres) + m_base * p.ld_res + col;
+    rld = p.ld_res;
+  }
+  const TADD* asrc = (EPI == EPI_GATE_RESID && p.addend) ? static_cast<const TADD*>(p.addend) + m_base * p.ld_add + col : nullptr;
+  float hv[32], av[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    hv[r] = 0.f; av[r] = 0.f;
+    if (FULL || r < rows_valid) {
+      hv[r] = ldf<TRES>(rsrc + r * rld);
+      if (EPI == EPI_GATE_RESID && asrc) av[r] = ldf<TADD>(asrc + r * p.ld_add);
+    }
+  }
+  float g = 0.f;
+  int b = b0, t = t0;
+  if (EPI == EPI_GATE_RESID) g = __ldg(p.gate + (int64_t)b0 * p.gate_bstride + col);
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    if (FULL || r < rows_valid) {
+      const float val = stage[r * STAGE_LD + lane] + bias;
+      float o;
+      if (EPI == EPI_GATE_RESID) o = __fadd_rn(hv[r], __fmul_rn(g, val + av[r]));
+      else if (EPI == EPI_EULER) o = __fadd_rn(hv[r], __fmul_rn(p.alpha, val));
+      else o = hv[r] + val;
+      stf<TRES>(rdst + r * rld, o);
+    }
+    if (!FULL && EPI == EPI_GATE_RESID) {  // rows may cross into the next sample: reload the gate there
+      if (++t == p.T_out) {
+        t = 0; ++b;
+        if (r + 1 < rows_valid) g = __ldg(p.gate + (int64_t)b * p.gate_bstride + col);
+      }
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_transposed(const TapGemm& p, float (&v)[32], float* stage, int lane,
+                                                    int64_t m_base, int rows_valid, int b0, int t0, int n) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * STAGE_LD + j] = v[j];
+  __syncwarp();
+  const int col = n + lane;
+  const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
+  const bool full = rows_valid == 32 && t0 + 32 <= p.T_out;
+  const bool res_bf16 = EPI == EPI_RESID && p.out_bf16;
+  const bool add_bf16 = EPI == EPI_GATE_RESID && p.addend_bf16 != 0;
+  if (res_bf16) {
+    if (full) epilogue_rows<EPI, true, bf16, bf16>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+    else epilogue_rows<EPI, false, bf16, bf16>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+  } else if (add_bf16) {
+    if (full) epilogue_rows<EPI, true, float, bf16>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+    else epilogue_rows<EPI, false, float, bf16>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+  } else {
+    if (full) epilogue_rows<EPI, true, float, float>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+    else epilogue_rows<EPI, false, float, float>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- the kernel
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TapGemm p,
                   const Sched sch) {
@@ -241,6 +345,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -254,7 +359,7 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], NUM_EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -327,36 +432,40 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue (warps 2..9: TMEM lane quarter = warp % 4, column half = (warp-2)/4) =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
+    float* stage = epi_stage + (warp - 2) * 32 * STAGE_LD;
+    constexpr bool kTransposed = (EPI == EPI_RESID || EPI == EPI_GATE_RESID || EPI == EPI_EULER);
     int it = 0;
+    if (kTransposed && (int)blockIdx.x < sch.num_tiles)
+      prefetch_epilogue_operands<BLOCK_N, EPI>(p, sch, blockIdx.x, quarter, half, lane);
     for (int tile = blockIdx.x; tile < sch.num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int nt = tile % sch.num_n_tiles, mt = tile / sch.num_n_tiles;
-      int64_t m;
-      int b;
-      bool valid;
-      if (sch.flatten) {
-        m = (int64_t)mt * BLOCK_M + row;
-        valid = m < (int64_t)p.B * p.T_out;
-        b = valid ? (int)(m / p.T_out) : 0;
-      } else {
-        b = mt / sch.tiles_m_per_b;
-        const int t = (mt % sch.tiles_m_per_b) * BLOCK_M + row;
-        valid = t < p.T_out;
-        m = (int64_t)b * p.T_out + t;
-      }
+      if (kTransposed && tile + (int)gridDim.x < sch.num_tiles)
+        prefetch_epilogue_operands<BLOCK_N, EPI>(p, sch, tile + gridDim.x, quarter, half, lane);
+      // the warp's first row: global row m_w, sample b_w, frame t_w; its valid rows are a prefix
+      int64_t m_w;
+      int b_w, t_w, rows_valid;
+      warp_rows(p, sch, mt, quarter, m_w, b_w, t_w, rows_valid);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-        if (valid) epilogue_row32(p, v, m, b, nt * BLOCK_N + ch * 32);
+        const int n = nt * BLOCK_N + ch * 32;
+        if (kTransposed) {
+          epilogue_transposed<EPI>(p, v, stage, lane, m_w, rows_valid, b_w, t_w, n);
+        } else {
+          if (lane < rows_valid) epilogue_direct<EPI>(p, v, m_w + lane, n);
+        }
       }
+      (void)row;
       tc_fence_before();
       mbar_arrive(&tmem_empty[as]);
     }
@@ -373,22 +482,54 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int BLOCK_N>
-void launch_cfg(const TapGemm& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const Sched& sch, int num_sms,
+template <int BLOCK_N, int EPI>
+void launch_one(const TapGemm& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const Sched& sch, int num_sms,
                 cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   const int grid = sch.num_tiles < num_sms ? sch.num_tiles : num_sms;
-  tapgemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p, sch);
+  tapgemm_tc_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p, sch);
   FLM_LAUNCH_CHECK();
+}
+
+template <int BLOCK_N>
+void launch_cfg(const TapGemm& p, const CUtensorMap& tmA, const CUtensorMap& tmB, const Sched& sch, int num_sms,
+                cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_NONE: launch_one<BLOCK_N, EPI_NONE>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_GELU: launch_one<BLOCK_N, EPI_GELU>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_SILU: launch_one<BLOCK_N, EPI_SILU>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_RELU: launch_one<BLOCK_N, EPI_RELU>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_RESID: launch_one<BLOCK_N, EPI_RESID>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_GATE_RESID: launch_one<BLOCK_N, EPI_GATE_RESID>(p, tmA, tmB, sch, num_sms, stream); break;
+    case EPI_EULER: launch_one<BLOCK_N, EPI_EULER>(p, tmA, tmB, sch, num_sms, stream); break;
+    default: throw Error(-1, "tapgemm_tc: unknown epilogue");
+  }
+}
+
+template <int BLOCK_N, int EPI>
+void set_attr_one() {
+  FLM_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<BLOCK_N>::SMEM_BYTES));
+}
+template <int BLOCK_N>
+void set_attr_all() {
+  set_attr_one<BLOCK_N, EPI_NONE>(); set_attr_one<BLOCK_N, EPI_GELU>(); set_attr_one<BLOCK_N, EPI_SILU>();
+  set_attr_one<BLOCK_N, EPI_RELU>(); set_attr_one<BLOCK_N, EPI_RESID>(); set_attr_one<BLOCK_N, EPI_GATE_RESID>();
+  set_attr_one<BLOCK_N, EPI_EULER>();
 }
 
 }  // namespace
 
 // must run once per process before the first launch (and outside any stream capture)
 void tapgemm_tc_init() {
-  FLM_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(tapgemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_BYTES));
+  set_attr_all<256>();
+  set_attr_all<128>();
+  set_attr_all<64>();
+}
+
+static int64_t sch_rows(const TapGemm& p) {
+  const bool flatten = p.ntaps == 1 && p.off0 == 0;
+  return flatten ? (int64_t)p.B * p.T_in : (int64_t)p.B * (((int64_t)p.T_out + BLOCK_M - 1) / BLOCK_M) * BLOCK_M;
 }
 
 bool tapgemm_tc_supported(const TapGemm& p) {
@@ -401,7 +542,12 @@ void launch_tapgemm_tc(const TapGemm& p, void* tma_encode, int num_sms, cudaStre
   FLM_REQUIRE(tma_encode != nullptr, "tapgemm_tc: cuTensorMapEncodeTiled entry point not resolved");
   if ((int64_t)p.B * p.T_out == 0) return;
   EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(tma_encode);
-  const int BN = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+  // widest N tile that still gives every SM a tile (small-M problems are latency bound: prefer more CTAs)
+  int BN = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+  {
+    const int64_t rows = sch_rows(p);
+    while (BN > 64 && p.N % (BN / 2) == 0 && ((rows + BLOCK_M - 1) / BLOCK_M) * (p.N / BN) < num_sms) BN /= 2;
+  }
   Sched sch;
   sch.flatten = (p.ntaps == 1 && p.off0 == 0) ? 1 : 0;
   sch.num_n_tiles = p.N / BN;

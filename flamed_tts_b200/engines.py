@@ -50,6 +50,21 @@ class Context:
     def stream(self):
         return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def profile(self, on):
+        """per-launch CUDA-event profiler of the library (launches inside CUDA graphs are not recorded)"""
+        check(self.lib.flm_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_read(self):
+        n = 8
+        buf = (ctypes.c_double * (n * 4))()
+        check(self.lib.flm_profile_read(self.handle, buf, n))
+        out = {}
+        for k in range(n):
+            cnt, ms, flops, byts = buf[k * 4:k * 4 + 4]
+            if cnt:
+                out[self.lib.flm_profile_class_name(k).decode()] = dict(launches=int(cnt), ms=ms, flops=flops, bytes=byts)
+        return out
+
 
 def _f32(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()

@@ -60,6 +60,8 @@ typedef struct {
 
 const char* flm_last_error(void);
 int flm_version(void);
+/* kernels launched by this library in this process so far (graph replays count their kernel nodes) */
+unsigned long long flm_launch_count(void);
 
 int flm_ctx_create(int device, flm_ctx** out);
 void flm_ctx_destroy(flm_ctx* ctx);
@@ -139,6 +141,14 @@ int64_t flm_codec_enc_frames(flm_codec_enc* h, int64_t S);
 /* wav (B,1,S) f32; out (B,256,T') f32 in the REFERENCE layout (channels-first) */
 int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S, float* out, flm_stream stream);
 
+/* ---------------------------------------------------------------- per-launch profiler (bench.py roofline)
+ * While enabled, every kernel launch made outside a CUDA-graph capture is bracketed by CUDA events on
+ * the launching stream.  flm_profile_read synchronises and fills out[class*4 + {0,1,2,3}] =
+ * {launch count, total ms, algorithmic FLOPs, algorithmic bytes} for the 8 kernel classes. */
+int flm_profile_enable(flm_ctx* ctx, int on);
+int flm_profile_read(flm_ctx* ctx, double* out, int n_classes);
+const char* flm_profile_class_name(int kclass);
+
 /* ---------------------------------------------------------------- generic kernels exposed for tests
  * out[b,t,n] = epi(sum_tap sum_k A[b, t*stride + off0 + tap*dil, k] * W[tap][n][k] + bias[n]),
  * rows outside [0,T_in) read as zero.  A (B,T_in,K) f32, W (ntaps,N,K) f32, out (B,T_out,N) f32.
@@ -147,6 +157,11 @@ int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S, float
 int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, const float* bias, int B, int T_in,
                      int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi, float* out,
                      flm_stream stream);
+
+/* micro-benchmark hook: `reps` launches of one tap-GEMM (pseudo-random operands) timed with CUDA events on
+ * `stream`; *out_ms = average ms per launch.  A (B,T,K), W (ntaps,N,K); epi 0..3 or 5 (gated residual). */
+int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, int N, int ntaps, int dil, int epi, int out_bf16,
+                      int reps, float* out_ms, flm_stream stream);
 
 #ifdef __cplusplus
 }

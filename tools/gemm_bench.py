@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Micro-benchmark of the tap-GEMM kernels (CUDA events, back-to-back launches)."""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from flamed_tts_b200 import _lib  # noqa: E402
+from flamed_tts_b200.engines import Context  # noqa: E402
+
+ctx = Context.get("cuda:0")
+lib = _lib.load_library()
+reps = int(os.environ.get("REPS", 20))
+cases = [  # mode, B, T, K, N, ntaps, dil, epi, out_bf16
+    (1, 1, 8192, 1024, 1024, 1, 1, 1, 1),
+    (1, 1, 76800, 1024, 1024, 1, 1, 1, 1),
+    (1, 1, 76800, 1024, 1024, 1, 1, 5, 0),
+    (1, 1, 76800, 1024, 1024, 1, 1, 0, 1),
+    (1, 64, 1200, 1024, 256, 3, 1, 0, 0),
+    (1, 1, 76800, 256, 1024, 1, 1, 0, 0),
+    (1, 64, 6000, 512, 512, 7, 3, 0, 1),
+    (1, 64, 120000, 64, 64, 7, 1, 0, 1),
+    (1, 1, 350, 1024, 1024, 1, 1, 1, 1),
+    (0, 1, 8192, 1024, 1024, 1, 1, 1, 0),
+]
+if len(sys.argv) > 1:
+    cases = [cases[int(a)] for a in sys.argv[1:]]
+for c in cases:
+    ms = ctypes.c_float(0)
+    _lib.check(lib.flm_tapgemm_bench(ctx.handle, *c, reps, ctypes.byref(ms), ctx.stream()))
+    mode, B, T, K, N, ntaps, dil, epi, ob = c
+    fl = 2.0 * B * T * K * N * ntaps
+    print("mode=%s M=%d K=%d N=%d taps=%d epi=%d: %.4f ms  %.1f TFLOP/s" %
+          ("bf16-tc" if mode else "fp32-fma", B * T, K, N, ntaps, epi, ms.value, fl / ms.value / 1e9), flush=True)
