@@ -99,7 +99,8 @@ def build_models(device, precision):
     from flamed_tts_b200 import synthetic as W
     cfg = load_cfg()
     model = Flamed(cfg).eval()
-    model.load_state_dict(W.make_flamed_state_dict(cfg["prior_generator"], cfg["prob_generator"], 0))
+    model.load_state_dict(W.make_flamed_state_dict(cfg["prior_generator"], cfg["prob_generator"], 0,
+                                                   dur_bias=W.BENCH_DUR_BIAS, sil_bias=W.BENCH_SIL_BIAS))
     dec = FACodecDecoder(in_channels=256, upsample_initial_channel=1024, ngf=32, up_ratios=[5, 5, 4, 2], vq_num_q_c=2,
                          vq_num_q_p=1, vq_num_q_r=3, vq_dim=256, codebook_dim=8).eval()
     dec.load_state_dict(W.make_codec_decoder_state_dict(0))
@@ -176,7 +177,8 @@ def cpu_baseline(args, n_utts=2, reps=1):
     from flamed_tts_b200 import synthetic as W
     cfg = load_cfg()
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = W.make_flamed_state_dict(cfg["prior_generator"], cfg["prob_generator"], 0)
+    sd = W.make_flamed_state_dict(cfg["prior_generator"], cfg["prob_generator"], 0, dur_bias=W.BENCH_DUR_BIAS,
+                                  sil_bias=W.BENCH_SIL_BIAS)
     dsd = W.make_codec_decoder_state_dict(0)
     wl = W.metadata_workload(args.utterances, 64, seed=0)
     order = sorted(range(len(wl["phonemes"])), key=lambda i: wl["phonemes"][i].numel())
@@ -230,7 +232,7 @@ def workload_config(args):
                         (args.utterances, args.max_batch),
             "nsteps_denoiser": args.nsteps_denoiser, "nsteps_durgen": args.nsteps_durgen,
             "temp_denoiser": args.temp_denoiser, "temp_durgen": args.temp_durgen, "precision": args.precision,
-            "weights": "random-init of configs/{prior,prob,codec}.yaml (seeded)", "noise": "device (torch cuda generator)",
+            "weights": "random-init of configs/{prior,prob,codec}.yaml (seeded; duration bias calibrated to 12 phonemes/s)", "noise": "device (torch cuda generator)",
             "l2": "per-step working set (>10 GB activations per batch) exceeds the 126 MB L2; no flush needed",
             "parallelism": "dp%d, one process per GPU, no collective in the loops, final NCCL waveform gather" % args.gpus}
 

@@ -50,6 +50,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
   if (qres != cudaDriverEntryPointSuccess || !c->tma_encode)
     throw Error(FLM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   tapgemm_tc_init();
+  kernels_norm_init();
   *out = c.release();
   FLM_API_END
 }
@@ -351,17 +352,8 @@ struct flm_denoiser : Engine {
       launch_dwconv(dw, s);
     }
     {
-      ProfScope ps(ctx, KC_GN_FINALIZE, s, 0, (double)B * dw_nchunk(L) * H * 8);
-      launch_gn_finalize(part.as<float>(), B, L, H, H, dw_nchunk(L), DW_TT, c.gn_w, c.gn_b, 1e-5f, gsc.as<float>(),
-                         gof.as<float>(), s);
-    }
-    GnApply ga;
-    memset(&ga, 0, sizeof(ga));
-    ga.x = bufD.p; ga.x_bf16 = b16; ga.y = bufG.p; ga.y_bf16 = b16; ga.scale = gsc.as<float>();
-    ga.offset = gof.as<float>(); ga.B = B; ga.L = L; ga.C = H;
-    {
       ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * eb);
-      launch_gn_apply(ga, s);
+      launch_gn_convnext(bufD.p, bufG.p, b16, part.as<float>(), c.gn_w, c.gn_b, 1e-5f, B, L, H, dw_nchunk(L), DW_TT, s);
     }
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
@@ -422,7 +414,7 @@ struct flm_denoiser : Engine {
     p.hres = target; p.ld_res = D; p.alpha = alpha;
     gemm(p, conv_out, bf(), s);
   }
-  int launches_per_step() const { return (bf() ? 2 : 1) + (int)blocks.size() * 9 + 8; }
+  int launches_per_step() const { return (bf() ? 2 : 1) + (int)blocks.size() * 8 + 7; }
 
   bool ensure(int B, int L, int nfe) {
     const int64_t M = (int64_t)B * L;

@@ -14,6 +14,7 @@ void launch_tapgemm_simt(const TapGemm& p, cudaStream_t stream);
 void launch_tapgemm_tc(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream);
 bool tapgemm_tc_supported(const TapGemm& p);
 void tapgemm_tc_init();
+void kernels_norm_init();
 
 // ---- row-wise LayerNorm (+ adaLN modulate): one warp per row, C % 128 == 0, C <= 1024
 // y = LN(x; w, b, eps) * (scale_plus_one + scale[bi]) + shift[bi],  bi = row / rows_per_batch
@@ -52,6 +53,10 @@ void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, f
 void launch_gn_finalize(const float* part, int B, int L, int C, int G, int nchunk, int chunk_rows,
                         const float* gamma, const float* beta, float eps, float* scale, float* offset,
                         cudaStream_t stream);
+
+// ---- ConvNeXt GroupNorm(C,C): merge of the depthwise kernel's partials fused with the affine apply
+void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, const float* gamma, const float* beta,
+                        float eps, int B, int L, int C, int nchunk, int chunk_rows, cudaStream_t stream);
 
 // ---- y = act(x*scale[b,c] + offset[b,c]) (*mask[b,t]) (+ res)   act: 0 none, 1 relu, 2 mish
 struct GnApply {

@@ -16,77 +16,167 @@ namespace {
 
 constexpr int LN_MAX_V = 8;  // C <= 1024
 
-__global__ void __launch_bounds__(256) ln_mod_kernel(LnMod p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= p.rows) return;
-  const int64_t row = warp;
-  const int nv = p.C >> 7;  // float4 per lane
-  const float* x = p.x + row * p.ldx;
-  float v[LN_MAX_V][4];
-  float s = 0.f;
+// Each warp owns a contiguous range of rows and streams them through a private ring of LN_DEPTH
+// shared-memory slots filled by 1-D bulk TMA copies (cp.async.bulk, one instruction per 4 KB row, completion
+// on an mbarrier), so LN_DEPTH rows per warp are always in flight from HBM regardless of register use.
+// The affine and adaLN terms are folded per sample into  y = xhat * A + Bv,  A = w*(spo+scale),
+// Bv = b*(spo+scale) + shift, kept in registers while the warp stays inside one sample.
+constexpr int LN_DEPTH = 3;
+constexpr int LN_WARPS = 16;
+
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64_t rows_per_warp) {
+  constexpr int C = NV * 128;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * LN_DEPTH * C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)LN_WARPS * LN_DEPTH * C * 4) + warp * LN_DEPTH;
+  const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp;
+  const int64_t r_begin = gw * rows_per_warp;
+  const int64_t r_end = min(p.rows, r_begin + rows_per_warp);
+  if (r_begin >= r_end) return;
+  if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
-    if (i < nv) {
-      ld4<float>(x + (i * 32 + lane) * 4, v[i]);
+    for (int d = 0; d < LN_DEPTH; ++d)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(&bars[d])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int64_t r, int slot) {  // lane 0 only
+    const uint32_t bar = ln_smem_u32(&bars[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * 4)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ln_smem_u32(ring + (size_t)slot * C)),
+                 "l"(p.x + r * p.ldx), "r"((uint32_t)(C * 4)), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < LN_DEPTH; ++d)
+      if (r_begin + d < r_end) issue(r_begin + d, d);
+  }
+  float A[NV][4], Bv[NV][4];
+  int cur_b = -1;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t row = r_begin; row < r_end; ++row) {
+    {
+      const uint32_t bar = ln_smem_u32(&bars[slot]);
+      uint32_t done;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(phase)
+            : "memory");
+      } while (!done);
+    }
+    float v[NV][4];
+    const float* xs = ring + (size_t)slot * C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ld4<float>(xs + (i * 32 + lane) * 4, v[i]);
+    __syncwarp();
+    if (lane == 0 && row + LN_DEPTH < r_end) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
+      issue(row + LN_DEPTH, slot);
+    }
+    const int bi = (int)(row / p.rows_per_batch);
+    if (bi != cur_b) {  // fold affine + modulation for this sample (warp-uniform branch)
+      cur_b = bi;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float w[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.w) { ld4<float>(p.w + c, w); ld4<float>(p.b + c, b); }
+        if (p.scale) {
+          float sc[4], sh[4];
+          ld4<float>(p.scale + (int64_t)bi * p.mod_bstride + c, sc);
+          ld4<float>(p.shift + (int64_t)bi * p.mod_bstride + c, sh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float m = p.scale_plus_one + sc[j];
+            A[i][j] = w[j] * m;
+            Bv[i][j] = fmaf(b[j], m, sh[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { A[i][j] = w[j]; Bv[i][j] = b[j]; }
+        }
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
       if (p.relu_in) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
       }
       s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
     }
-  }
-  const float mean = warp_sum(s) / (float)p.C;
-  float q = 0.f;
+    const float mean = warp_sum(s) * (1.0f / (float)C);
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
-    if (i < nv) {
+    for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float d = v[i][j] - mean;
-        q = fmaf(d, d, q);
+        v[i][j] -= mean;
+        q = fmaf(v[i][j], v[i][j], q);
       }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / (float)p.C + p.eps);
-  const int bi = (int)(row / p.rows_per_batch);
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + p.eps);
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V; ++i) {
-    if (i < nv) {
+    for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = (v[i][j] - mean) * rstd;
-      if (p.w) {
-        float w[4], b[4];
-        ld4<float>(p.w + c, w);
-        ld4<float>(p.b + c, b);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaf(o[j], w[j], b[j]);
-      }
-      if (p.scale) {
-        float sc[4], sh[4];
-        ld4<float>(p.scale + (int64_t)bi * p.mod_bstride + c, sc);
-        ld4<float>(p.shift + (int64_t)bi * p.mod_bstride + c, sh);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fmaf(o[j], p.scale_plus_one + sc[j], sh[j]);
-      }
+      for (int j = 0; j < 4; ++j) o[j] = fmaf(v[i][j] * rstd, A[i][j], Bv[i][j]);
       if (p.y_bf16)
         st4<bf16>(static_cast<bf16*>(p.y) + row * p.ldy + c, o);
       else
         st4<float>(static_cast<float*>(p.y) + row * p.ldy + c, o);
     }
+    if (++slot == LN_DEPTH) { slot = 0; phase ^= 1; }
   }
+}
+
+template <int NV>
+constexpr int ln_smem_bytes() { return LN_WARPS * LN_DEPTH * NV * 128 * 4 + LN_WARPS * LN_DEPTH * 8; }
+template <int NV>
+void ln_set_attr() {
+  FLM_CUDA(cudaFuncSetAttribute(ln_mod_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<NV>()));
+}
+
+template <int NV>
+void ln_launch(const LnMod& p, int sms, cudaStream_t stream) {
+  constexpr int smem = ln_smem_bytes<NV>();
+  int64_t blocks = (p.rows + LN_WARPS - 1) / LN_WARPS;
+  if (blocks > sms) blocks = sms;
+  const int64_t total_warps = blocks * LN_WARPS;
+  const int64_t rpw = (p.rows + total_warps - 1) / total_warps;
+  ln_mod_kernel<NV><<<(unsigned)blocks, LN_WARPS * 32, smem, stream>>>(p, rpw);
 }
 
 }  // namespace
 
 void launch_ln_mod(const LnMod& p, cudaStream_t stream) {
   FLM_REQUIRE(p.C % 128 == 0 && p.C <= 128 * LN_MAX_V, "ln_mod: C must be a multiple of 128 and <= 1024");
+  FLM_REQUIRE(p.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0, "ln_mod: input rows must be 16-byte aligned");
   if (p.rows == 0) return;
-  const int warps_per_block = 8;
-  const unsigned grid = (unsigned)((p.rows + warps_per_block - 1) / warps_per_block);
-  ln_mod_kernel<<<grid, warps_per_block * 32, 0, stream>>>(p);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  switch (p.C >> 7) {
+    case 1: ln_launch<1>(p, sms, stream); break;
+    case 2: ln_launch<2>(p, sms, stream); break;
+    case 3: ln_launch<3>(p, sms, stream); break;
+    case 4: ln_launch<4>(p, sms, stream); break;
+    case 8: ln_launch<8>(p, sms, stream); break;
+    default: throw Error(-1, "ln_mod: C must be 128, 256, 384, 512 or 1024");
+  }
   FLM_LAUNCH_CHECK();
 }
 
@@ -116,15 +206,35 @@ __device__ __forceinline__ void st2<bf16>(bf16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-// thread = 2 adjacent channels x DW_TT consecutive frames; block = 128 threads = 256 channels.
-// grid = (C/256, nchunk, B).  Zero padding at the two ends of the padded batch row range [0,L).
+// block = 128 threads = 256 channels x DW_TT frames; thread = 2 adjacent channels x DW_TT frames.
+// The (DW_TT + KW - 1) x 256 input tile (with its 15-frame halo on both sides, zero outside [0,L)) is staged
+// in shared memory with 16-byte cp.async issued up front by all threads, so every global load of the block
+// is in flight at once; the 31-tap sliding window then runs out of shared memory with the tap weights and
+// the 2 x DW_TT accumulators in registers.  grid = (C/256, nchunk, B).
 template <typename T, int KW>
 __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   constexpr int PAD = KW / 2;
-  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  constexpr int ROWS = DW_TT + KW - 1;
+  constexpr int VPR = 256 * (int)sizeof(T) / 16;  // 16-byte vectors per tile row
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  T* tile = reinterpret_cast<T*>(dw_smem);
+  const int c0 = blockIdx.x * 256;
+  const int c = c0 + threadIdx.x * 2;
   const int chunk = blockIdx.y, b = blockIdx.z;
   const int t0 = chunk * DW_TT;
-  if (c >= p.C) return;
+  const T* xb = static_cast<const T*>(p.x) + (int64_t)b * p.L * p.C + c0;
+  for (int v = threadIdx.x; v < ROWS * VPR; v += 128) {
+    const int row = v / VPR, col = v % VPR;
+    const int t = t0 - PAD + row;
+    uint8_t* dst = dw_smem + ((size_t)row * VPR + col) * 16;
+    if (t >= 0 && t < p.L) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (int64_t)t * p.C) + col * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   float w0[KW], w1[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
@@ -134,12 +244,13 @@ __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   float a0[DW_TT], a1[DW_TT];
 #pragma unroll
   for (int j = 0; j < DW_TT; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
-  const T* xb = static_cast<const T*>(p.x) + (int64_t)b * p.L * p.C + c;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const T* xs = tile + threadIdx.x * 2;
 #pragma unroll
-  for (int r = 0; r < DW_TT + KW - 1; ++r) {
-    const int t = t0 - PAD + r;
-    float x0 = 0.f, x1 = 0.f;
-    if (t >= 0 && t < p.L) ld2<T>(xb + (int64_t)t * p.C, x0, x1);
+  for (int r = 0; r < ROWS; ++r) {
+    float x0, x1;
+    ld2<T>(xs + r * 256, x0, x1);
 #pragma unroll
     for (int j = 0; j < DW_TT; ++j) {
       const int tap = r - j;  // compile-time after unrolling
@@ -186,10 +297,11 @@ void launch_dwconv(const DwConv& p, cudaStream_t stream) {
   FLM_REQUIRE(p.C % 256 == 0, "dwconv: C must be a multiple of 256");
   if (p.B == 0 || p.L == 0) return;
   dim3 grid(p.C / 256, dw_nchunk(p.L), p.B);
+  constexpr int ROWS = DW_TT + 31 - 1;
   if (p.io_bf16)
-    dwconv_kernel<bf16, 31><<<grid, 128, 0, stream>>>(p);
+    dwconv_kernel<bf16, 31><<<grid, 128, ROWS * 256 * 2, stream>>>(p);
   else
-    dwconv_kernel<float, 31><<<grid, 128, 0, stream>>>(p);
+    dwconv_kernel<float, 31><<<grid, 128, ROWS * 256 * 4, stream>>>(p);
   FLM_LAUNCH_CHECK();
 }
 
@@ -292,7 +404,87 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApply p) {
   st4<TY>(static_cast<TY*>(p.y) + row * p.C + c, v);
 }
 
+// GroupNorm(C,C) of the ConvNeXt block, statistics merge fused in: block = (32 rows, sample b), thread = 4
+// channels.  Prologue: Chan-merge (fp64) of the per-chunk (mean, M2) partials the depthwise kernel wrote
+// -> scale = gamma*rstd, offset = beta - mean*scale in registers; body: y = x*scale + offset, 8 B/16 B vectors.
+constexpr int GNF_ROWS = 128;
+template <typename T>
+__global__ void __launch_bounds__(256) gn_convnext_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                          const float* __restrict__ part, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, int L, int C,
+                                                          int nchunk, int chunk_rows) {
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * GNF_ROWS;
+  const int nrows = min(GNF_ROWS, L - r0);
+  for (int c = threadIdx.x * 4; c < C; c += 256 * 4) {
+    // two passes over the partials, no divisions: mean = sum(n_k m_k)/N; M2 = sum(q_k + n_k (m_k - mean)^2)
+    const float* pbase = part + ((int64_t)b * nchunk * C + c) * 2;
+    double sm[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nchunk; ++k) {
+      const float* pp = pbase + (int64_t)k * C * 2;
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pp));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pp + 4));
+      const double nb = (double)min(chunk_rows, L - k * chunk_rows);
+      sm[0] += nb * p0.x; sm[1] += nb * p0.z; sm[2] += nb * p1.x; sm[3] += nb * p1.z;
+    }
+    const double inv_n = 1.0 / (double)L;
+    double mean[4], m2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mean[j] = sm[j] * inv_n;
+    for (int k = 0; k < nchunk; ++k) {
+      const float* pp = pbase + (int64_t)k * C * 2;
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pp));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pp + 4));
+      const double nb = (double)min(chunk_rows, L - k * chunk_rows);
+      const double d0 = p0.x - mean[0], d1 = p0.z - mean[1], d2 = p1.x - mean[2], d3 = p1.z - mean[3];
+      m2[0] += p0.y + nb * d0 * d0; m2[1] += p0.w + nb * d1 * d1;
+      m2[2] += p1.y + nb * d2 * d2; m2[3] += p1.w + nb * d3 * d3;
+    }
+    float ga[4], be[4], sc[4], of[4];
+    ld4<float>(gamma + c, ga);
+    ld4<float>(beta + c, be);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float rstd = rsqrtf((float)(m2[j] * inv_n) + eps);
+      sc[j] = ga[j] * rstd;
+      of[j] = be[j] - (float)mean[j] * sc[j];
+    }
+    const T* xp = x + ((int64_t)b * L + r0) * C + c;
+    T* yp = y + ((int64_t)b * L + r0) * C + c;
+#pragma unroll 8
+    for (int r = 0; r < nrows; ++r) {
+      float v[4];
+      ld4<T>(xp + (int64_t)r * C, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = fmaf(v[j], sc[j], of[j]);
+      st4<T>(yp + (int64_t)r * C, v);
+    }
+  }
+}
+
 }  // namespace
+
+void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, const float* gamma, const float* beta,
+                        float eps, int B, int L, int C, int nchunk, int chunk_rows, cudaStream_t stream) {
+  FLM_REQUIRE(C % 4 == 0, "gn_convnext: C % 4 != 0");
+  if (B == 0 || L == 0) return;
+  dim3 grid((L + GNF_ROWS - 1) / GNF_ROWS, B);
+  if (io_bf16)
+    gn_convnext_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), part, gamma,
+                                                       beta, eps, L, C, nchunk, chunk_rows);
+  else
+    gn_convnext_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), part,
+                                                        gamma, beta, eps, L, C, nchunk, chunk_rows);
+  FLM_LAUNCH_CHECK();
+}
+
+// opt-in shared-memory sizes; must run once per process outside any stream capture (flm_ctx_create)
+void kernels_norm_init() {
+  ln_set_attr<1>(); ln_set_attr<2>(); ln_set_attr<3>(); ln_set_attr<4>(); ln_set_attr<8>();
+  constexpr int ROWS = DW_TT + 31 - 1;
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<float, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 4));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<bf16, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 2));
+}
 
 void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, float* part, cudaStream_t stream) {
   FLM_REQUIRE(C % G == 0, "group_stats: C % G != 0");

@@ -30,6 +30,9 @@ import numpy as np
 import torch
 
 N_SYMBOLS = 360  # len(flamed.text.symbols.symbols), SURVEY.md section 1
+# output biases of the duration / silence generators that give LibriSpeech-like speaking rates with these
+# random weights (measured: ~6.7 frames per phoneme = 12 phonemes/s at 80 frames/s, temperature 0.3)
+BENCH_DUR_BIAS, BENCH_SIL_BIAS = 1.35, -0.5
 
 
 def _gen(name, seed):
