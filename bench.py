@@ -127,7 +127,8 @@ def make_batches(args, rank, model, enc, dec, device):
             timbres.append(spk.cpu())
         codes, timbres = torch.cat(codes), torch.cat(timbres)
     batches = []
-    for idx in W.bucket_by_length(wl["phonemes"], args.max_batch):
+    from flamed_tts_b200.parallel import bucket_by_length
+    for idx in bucket_by_length([p.numel() for p in wl["phonemes"]], args.max_batch):
         ph = torch.nn.utils.rnn.pad_sequence([wl["phonemes"][i] for i in idx], batch_first=True, padding_value=0)
         sl = torch.tensor([wl["phonemes"][i].numel() for i in idx], dtype=torch.long)
         pi = [int(wl["prompt_of"][i]) for i in idx]
@@ -157,16 +158,9 @@ def run_step(model, dec, batches, args, device, from_host, host_out=None):
 
 
 def gather_wavs(wavs, rank, world):
-    """the path's only collective: final NCCL gather of the waveforms to rank 0 (padded to the max size)"""
-    import torch.distributed as dist
-    flat = torch.cat([w.reshape(-1) for w in wavs])
-    n = torch.tensor([flat.numel()], device=flat.device, dtype=torch.int64)
-    dist.all_reduce(n, op=dist.ReduceOp.MAX)
-    buf = torch.zeros(int(n.item()), device=flat.device, dtype=flat.dtype)
-    buf[: flat.numel()] = flat
-    out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-    dist.gather(buf, out, dst=0)
-    return out
+    """the path's only collective: final NCCL gather of the waveforms to rank 0"""
+    from flamed_tts_b200.parallel import gather_waveforms
+    return gather_waveforms(wavs, rank, world)
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline

@@ -132,7 +132,7 @@ class Flamed(nn.Module):
                 FACodecDecoder.from_pretrained(codec_cfg["decoder"]).eval())
 
     def read_lexicon(self, lexicon_path=None):
-        path = lexicon_path or _DEFAULT_LEXICON
+        path = lexicon_path or os.environ.get("FLAMED_LEXICON") or _DEFAULT_LEXICON
         lexicon = {}
         if not os.path.exists(path):  # the blob is not shipped (reference: .MISSING_LARGE_BLOBS)
             return lexicon

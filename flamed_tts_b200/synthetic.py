@@ -312,10 +312,3 @@ def metadata_workload(n_utterances=256, n_prompts=64, seed=0, dur_range=(2.0, 15
     prompts = torch.from_numpy((prng.standard_normal((n_prompts, 1, 48000)) * 0.1).astype(np.float32))
     prompt_of = np.arange(n_utterances) % n_prompts
     return dict(durations_s=dur, phonemes=phonemes, prompts_wav=prompts, prompt_of=prompt_of)
-
-
-def bucket_by_length(phonemes, max_batch=64):
-    """length-bucketed batches: sort by phoneme count (a proxy of the frame count), cut into chunks of
-    <= max_batch.  Returns a list of index arrays (longest bucket first)."""
-    order = sorted(range(len(phonemes)), key=lambda i: -int(phonemes[i].numel()))
-    return [order[i:i + max_batch] for i in range(0, len(order), max_batch)]
