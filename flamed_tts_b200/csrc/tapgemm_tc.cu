@@ -308,6 +308,9 @@ __device__ __forceinline__ void epilogue_rows(const TapGemm& p, const float* sta
 template <int EPI>
 __device__ __forceinline__ void epilogue_transposed(const TapGemm& p, float (&v)[32], float* stage, int lane,
                                                     int64_t m_base, int rows_valid, int b0, int t0, int n) {
+  // a quarter that lies entirely beyond the last row (ragged last tile) has nothing to do; its sample index
+  // b0 would be out of range, so no operand (gate, bias, stream) may be touched.  rows_valid is warp-uniform.
+  if (rows_valid <= 0) return;
 #pragma unroll
   for (int j = 0; j < 32; ++j) stage[lane * STAGE_LD + j] = v[j];
   __syncwarp();

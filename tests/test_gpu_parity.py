@@ -397,3 +397,18 @@ def test_sample_single_utterance_with_raw_prompt(dropin):
         assert np.isfinite(r["wav"]).all() and np.abs(r["wav"]).max() <= 1.0
         outs.append(r["wav"])
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_denoiser_ragged_last_tile_many_steps(engines, flamed_sd):
+    """regression: B*L with a partially empty last 128-row tile (rows % 128 in (0, 96]) at the LAST Euler step used
+    to read the adaLN gate of a non-existent sample (out-of-bounds).  Also checks the loop against the oracle."""
+    torch.manual_seed(17)
+    B, L, nfe = 3, 53, 6  # 159 rows: last tile has 31 valid rows -> three empty quarters
+    cond, spk, noise = torch.relu(torch.randn(B, L, 256)), torch.randn(B, 256), torch.randn(B, L, 256)
+    with torch.inference_mode():
+        ref = O.denoiser_sample(flamed_sd, "prob_generator", cond, spk, noise, nfe, 0.3).transpose(1, 2)
+    ts = torch.linspace(0, 1, nfe + 1)
+    for rep in range(3):
+        lat = engines["den16"].sample(cond, spk, noise, ts, 0.3, use_graph=False)
+    assert _rel(lat, ref) < 1e-2
+    assert _rel(engines["den32"].sample(cond, spk, noise, ts, 0.3, use_graph=False), ref) < 1e-5
