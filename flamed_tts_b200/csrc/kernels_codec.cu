@@ -44,48 +44,59 @@ __device__ __forceinline__ float snake(float u, float a, float invb) {
   const float sn = FAST ? __sinf(u * a) : sinf(u * a);
   return fmaf(sn * sn, invb, u);
 }
+// both channels of a thread at once: s = u + sin^2(a u) * invb on a packed pair
+template <bool FAST>
+__device__ __forceinline__ f32x2 snake2(f32x2 u2, f32x2 a2, f32x2 ib2) {
+  float t0, t1;
+  unpack2(mul2(u2, a2), t0, t1);
+  const float s0 = FAST ? __sinf(t0) : sinf(t0), s1 = FAST ? __sinf(t1) : sinf(t1);
+  return fma2(pack2(s0 * s0, s1 * s1), ib2, u2);
+}
 
 // u at up-sampled index m (0 <= m < 2T) from the clamped input window xw[i] = x[clamp(n0-5+i)]
-// (static indices only).  q = m - (2*n0 - 5) is the local index.
+// (static indices only).  q = m - (2*n0 - 5) is the local index; fu2[k] = (2 fu[k], 2 fu[k]).
 template <int Q>
-__device__ __forceinline__ float upsample_at(const float (&xw)[ACT_TT + 10], const float (&fu)[12]) {
-  // m = 2*n0 - 5 + Q.  m odd <=> Q even.  j = floor(m/2) = n0 - 3 + (Q+1)/2 (Q even: m = 2j+1)
-  float acc = 0.f;
+__device__ __forceinline__ f32x2 upsample_at(const f32x2 (&xw)[ACT_TT + 10], const f32x2 (&fu2)[12]) {
+  f32x2 acc = 0ull;
   if ((Q & 1) == 0) {
-    // odd m = 2j+1, j = n0 - 3 + Q/2: taps x[j-2+i] -> window index (j-2+i) - (n0-5) = Q/2 + i
+    // odd m = 2j+1, j = n0 - 3 + Q/2: taps x[j-2+i] -> window index Q/2 + i
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc = fmaf(xw[Q / 2 + i], fu[10 - 2 * i], acc);
+    for (int i = 0; i < 6; ++i) acc = fma2(xw[Q / 2 + i], fu2[10 - 2 * i], acc);
   } else {
     // even m = 2j, j = n0 - 3 + (Q+1)/2: taps x[j-3+i] -> window index (Q+1)/2 - 1 + i
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc = fmaf(xw[(Q + 1) / 2 - 1 + i], fu[11 - 2 * i], acc);
+    for (int i = 0; i < 6; ++i) acc = fma2(xw[(Q + 1) / 2 - 1 + i], fu2[11 - 2 * i], acc);
   }
-  return 2.0f * acc;
+  return acc;
 }
 
 template <bool FAST, int Q>
 struct SFill {
-  __device__ static __forceinline__ void run(const float (&xw0)[ACT_TT + 10], const float (&xw1)[ACT_TT + 10],
-                                             const float (&fu)[12], float a0, float a1, float ib0, float ib1, int mbase,
-                                             int twoT, float sf0, float sf1, float sl0, float sl1,
-                                             float (&s0)[2 * ACT_TT + 10], float (&s1)[2 * ACT_TT + 10]) {
+  __device__ static __forceinline__ void run(const f32x2 (&xw)[ACT_TT + 10], const f32x2 (&fu2)[12], f32x2 a2, f32x2 ib2,
+                                             int mbase, int twoT, f32x2 sf, f32x2 sl, f32x2 (&s)[2 * ACT_TT + 10]) {
     const int m = mbase + Q;
-    float v0 = snake<FAST>(upsample_at<Q>(xw0, fu), a0, ib0);
-    float v1 = snake<FAST>(upsample_at<Q>(xw1, fu), a1, ib1);
-    if (m < 0) { v0 = sf0; v1 = sf1; }
-    if (m > twoT - 1) { v0 = sl0; v1 = sl1; }
-    s0[Q] = v0; s1[Q] = v1;
-    SFill<FAST, Q + 1>::run(xw0, xw1, fu, a0, a1, ib0, ib1, mbase, twoT, sf0, sf1, sl0, sl1, s0, s1);
+    f32x2 v = snake2<FAST>(upsample_at<Q>(xw, fu2), a2, ib2);
+    if (m < 0) v = sf;
+    if (m > twoT - 1) v = sl;
+    s[Q] = v;
+    SFill<FAST, Q + 1>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
   }
 };
 template <bool FAST>
 struct SFill<FAST, 2 * ACT_TT + 10> {
-  __device__ static __forceinline__ void run(const float (&)[ACT_TT + 10], const float (&)[ACT_TT + 10],
-                                             const float (&)[12], float, float, float, float, int, int, float, float,
-                                             float, float, float (&)[2 * ACT_TT + 10], float (&)[2 * ACT_TT + 10]) {}
+  __device__ static __forceinline__ void run(const f32x2 (&)[ACT_TT + 10], const f32x2 (&)[12], f32x2, f32x2, int, int,
+                                             f32x2, f32x2, f32x2 (&)[2 * ACT_TT + 10]) {}
 };
 
-// blockDim = (bx channel pairs, by time runs); grid = (C/2/bx, ceil(T/(by*ACT_TT)), B)
+template <typename T>
+__device__ __forceinline__ f32x2 ld_pair2(const T* p) {
+  float a, b;
+  ldpair<T>(p, a, b);
+  return pack2(a, b);
+}
+
+// blockDim = (bx channel pairs, by time runs); grid = (C/2/bx, ceil(T/(by*ACT_TT)), B).  The two channels of a
+// thread travel as packed fp32x2 (FFMA2).
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -94,53 +105,47 @@ __global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
   if (c >= p.C || n0 >= p.T) return;
   const int Tm1 = p.T - 1;
   const T* xb = static_cast<const T*>(p.x) + (int64_t)b * p.T * p.C + c;
-  float fu[12], fd[12];
+  f32x2 fu2[12], fd2[12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) { fu[k] = p.fu[k]; fd[k] = p.fd[k]; }
-  const float2 av = *reinterpret_cast<const float2*>(p.a + c);
-  const float2 ib = *reinterpret_cast<const float2*>(p.invb + c);
-  float xw0[ACT_TT + 10], xw1[ACT_TT + 10];
+  for (int k = 0; k < 12; ++k) {
+    fu2[k] = pack2(2.0f * p.fu[k], 2.0f * p.fu[k]);  // up-sampler gain 2 folded in (exact)
+    fd2[k] = pack2(p.fd[k], p.fd[k]);
+  }
+  const f32x2 a2 = *reinterpret_cast<const f32x2*>(p.a + c);
+  const f32x2 ib2 = *reinterpret_cast<const f32x2*>(p.invb + c);
+  f32x2 xw[ACT_TT + 10];
 #pragma unroll
   for (int i = 0; i < ACT_TT + 10; ++i) {
     const int t = min(max(n0 - 5 + i, 0), Tm1);
-    ldpair<T>(xb + (int64_t)t * p.C, xw0[i], xw1[i]);
+    xw[i] = ld_pair2<T>(xb + (int64_t)t * p.C);
   }
   // replicate padding of the activated up-sampled signal: s[-k] = s[0], s[2T-1+k] = s[2T-1]
   const int mbase = 2 * n0 - 5;
   const int twoT = 2 * p.T;
-  float sf0 = 0.f, sf1 = 0.f, sl0 = 0.f, sl1 = 0.f;
+  f32x2 sf = 0ull, sl = 0ull;
   if (mbase < 0) {  // s[0] = snake(u[0]), u[0] = 2*sum x[clamp(-3+i)] fu[11-2i]
-    float u0 = 0.f, u1 = 0.f;
+    f32x2 u = 0ull;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float e0, e1;
-      ldpair<T>(xb + (int64_t)min(max(i - 3, 0), Tm1) * p.C, e0, e1);
-      u0 = fmaf(e0, fu[11 - 2 * i], u0); u1 = fmaf(e1, fu[11 - 2 * i], u1);
-    }
-    sf0 = snake<FAST>(2.0f * u0, av.x, ib.x); sf1 = snake<FAST>(2.0f * u1, av.y, ib.y);
+    for (int i = 0; i < 6; ++i) u = fma2(ld_pair2<T>(xb + (int64_t)min(max(i - 3, 0), Tm1) * p.C), fu2[11 - 2 * i], u);
+    sf = snake2<FAST>(u, a2, ib2);
   }
   if (mbase + 2 * ACT_TT + 9 > twoT - 1) {  // s[2T-1] = snake(u[2(T-1)+1])
-    float u0 = 0.f, u1 = 0.f;
+    f32x2 u = 0ull;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float e0, e1;
-      ldpair<T>(xb + (int64_t)min(max(Tm1 - 2 + i, 0), Tm1) * p.C, e0, e1);
-      u0 = fmaf(e0, fu[10 - 2 * i], u0); u1 = fmaf(e1, fu[10 - 2 * i], u1);
-    }
-    sl0 = snake<FAST>(2.0f * u0, av.x, ib.x); sl1 = snake<FAST>(2.0f * u1, av.y, ib.y);
+    for (int i = 0; i < 6; ++i) u = fma2(ld_pair2<T>(xb + (int64_t)min(max(Tm1 - 2 + i, 0), Tm1) * p.C), fu2[10 - 2 * i], u);
+    sl = snake2<FAST>(u, a2, ib2);
   }
-  float s0[2 * ACT_TT + 10], s1[2 * ACT_TT + 10];
-  SFill<FAST, 0>::run(xw0, xw1, fu, av.x, av.y, ib.x, ib.y, mbase, twoT, sf0, sf1, sl0, sl1, s0, s1);
+  f32x2 s[2 * ACT_TT + 10];
+  SFill<FAST, 0>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
   T* yb = static_cast<T*>(p.y) + (int64_t)b * p.T * p.C + c;
 #pragma unroll
   for (int j = 0; j < ACT_TT; ++j) {
     if (n0 + j < p.T) {
-      float y0 = 0.f, y1 = 0.f;
+      f32x2 y = 0ull;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        y0 = fmaf(s0[2 * j + k], fd[k], y0);
-        y1 = fmaf(s1[2 * j + k], fd[k], y1);
-      }
+      for (int k = 0; k < 12; ++k) y = fma2(s[2 * j + k], fd2[k], y);
+      float y0, y1;
+      unpack2(y, y0, y1);
       stpair<T>(yb + (int64_t)(n0 + j) * p.C, y0, y1);
     }
   }

@@ -209,83 +209,96 @@ __device__ __forceinline__ void st2<bf16>(bf16* p, float a, float b) {
 // block = 128 threads = 256 channels x DW_TT frames; thread = 2 adjacent channels x DW_TT frames.
 // The (DW_TT + KW - 1) x 256 input tile (with its 15-frame halo on both sides, zero outside [0,L)) is staged
 // in shared memory with 16-byte cp.async issued up front by all threads, so every global load of the block
-// is in flight at once; the 31-tap sliding window then runs out of shared memory with the tap weights and
-// the 2 x DW_TT accumulators in registers.  grid = (C/256, nchunk, B).
+// is in flight at once; the 31-tap sliding window then runs out of shared memory.  The two channels of a
+// thread are processed as packed fp32x2 (FFMA2: both IEEE fp32 FMAs in one instruction), tap weights and the
+// DW_TT accumulators in 64-bit registers.  grid = (C/256, nchunk, B).
+template <typename T>
+__device__ __forceinline__ f32x2 lds_pair(const T* p);
+template <>
+__device__ __forceinline__ f32x2 lds_pair<float>(const float* p) {
+  return *reinterpret_cast<const f32x2*>(p);
+}
+template <>
+__device__ __forceinline__ f32x2 lds_pair<bf16>(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);  // bf16 -> fp32 is a 16-bit shift
+  return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
 template <typename T, int KW>
 __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   constexpr int PAD = KW / 2;
   constexpr int ROWS = DW_TT + KW - 1;
-  constexpr int VPR = 256 * (int)sizeof(T) / 16;  // 16-byte vectors per tile row
+  constexpr int VPR = 256 * (int)sizeof(T) / 16;  // 16-byte vectors per tile row (32 bf16 / 64 fp32)
+  constexpr int RPI = 128 / VPR;                  // tile rows covered per cp.async sweep of the block
   extern __shared__ __align__(16) uint8_t dw_smem[];
   T* tile = reinterpret_cast<T*>(dw_smem);
   const int c0 = blockIdx.x * 256;
   const int c = c0 + threadIdx.x * 2;
   const int chunk = blockIdx.y, b = blockIdx.z;
   const int t0 = chunk * DW_TT;
-  const T* xb = static_cast<const T*>(p.x) + (int64_t)b * p.L * p.C + c0;
-  for (int v = threadIdx.x; v < ROWS * VPR; v += 128) {
-    const int row = v / VPR, col = v % VPR;
-    const int t = t0 - PAD + row;
-    uint8_t* dst = dw_smem + ((size_t)row * VPR + col) * 16;
-    if (t >= 0 && t < p.L) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(xb + (int64_t)t * p.C) + col * 16;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
-    } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  {
+    const int col = threadIdx.x % VPR, row0 = threadIdx.x / VPR;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(static_cast<const T*>(p.x) + ((int64_t)b * p.L + (t0 - PAD + row0)) * p.C + c0) + col * 16;
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(dw_smem) + (row0 * VPR + col) * 16;
+    const int64_t sstep = (int64_t)RPI * p.C * sizeof(T);
+#pragma unroll 4
+    for (int row = row0; row < ROWS; row += RPI) {
+      const int t = t0 - PAD + row;
+      if (t >= 0 && t < p.L) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+      else asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0));
+      src += sstep;
+      dst += RPI * VPR * 16;
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  float w0[KW], w1[KW];
+  f32x2 w2[KW];
 #pragma unroll
-  for (int k = 0; k < KW; ++k) {
-    float2 t = *reinterpret_cast<const float2*>(p.w + (int64_t)k * p.C + c);
-    w0[k] = t.x; w1[k] = t.y;
-  }
-  float a0[DW_TT], a1[DW_TT];
+  for (int k = 0; k < KW; ++k) w2[k] = *reinterpret_cast<const f32x2*>(p.w + (int64_t)k * p.C + c);
+  f32x2 acc[DW_TT];
 #pragma unroll
-  for (int j = 0; j < DW_TT; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+  for (int j = 0; j < DW_TT; ++j) acc[j] = 0ull;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const T* xs = tile + threadIdx.x * 2;
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    float x0, x1;
-    ld2<T>(xs + r * 256, x0, x1);
+    const f32x2 x2 = lds_pair<T>(xs + r * 256);
 #pragma unroll
     for (int j = 0; j < DW_TT; ++j) {
       const int tap = r - j;  // compile-time after unrolling
-      if (tap >= 0 && tap < KW) {
-        a0[j] = fmaf(w0[tap], x0, a0[j]);
-        a1[j] = fmaf(w1[tap], x1, a1[j]);
-      }
+      if (tap >= 0 && tap < KW) acc[j] = fma2(w2[tap], x2, acc[j]);
     }
   }
-  const float2 bias = *reinterpret_cast<const float2*>(p.bias + c);
+  const f32x2 bias2 = *reinterpret_cast<const f32x2*>(p.bias + c);
   const int nvalid = min(DW_TT, p.L - t0);
-  T* yb = static_cast<T*>(p.y) + (int64_t)b * p.L * p.C + c;
-  float s0 = 0.f, s1 = 0.f;
+  T* yb = static_cast<T*>(p.y) + ((int64_t)b * p.L + t0) * p.C + c;
+  f32x2 s2 = 0ull;
 #pragma unroll
   for (int j = 0; j < DW_TT; ++j) {
-    a0[j] += bias.x; a1[j] += bias.y;
+    acc[j] = add2(acc[j], bias2);
     if (j < nvalid) {
-      // statistics are taken on the values the next kernel will read back (storage precision)
-      if (sizeof(T) == 2) {
-        a0[j] = __bfloat162float(__float2bfloat16_rn(a0[j]));
-        a1[j] = __bfloat162float(__float2bfloat16_rn(a1[j]));
-      }
-      st2<T>(yb + (int64_t)(t0 + j) * p.C, a0[j], a1[j]);
-      s0 += a0[j]; s1 += a1[j];
+      float a0, a1;
+      unpack2(acc[j], a0, a1);
+      st2<T>(yb + (int64_t)j * p.C, a0, a1);
+      s2 = add2(s2, acc[j]);
     }
   }
-  const float m0 = s0 / (float)nvalid, m1 = s1 / (float)nvalid;
-  float q0 = 0.f, q1 = 0.f;
+  // per-chunk (mean, M2) of the fp32 results (two-pass, no cancellation); merged later in fp64
+  float s0, s1;
+  unpack2(s2, s0, s1);
+  const float inv = 1.0f / (float)nvalid;
+  const float m0 = s0 * inv, m1 = s1 * inv;
+  const f32x2 negm = pack2(-m0, -m1);
+  f32x2 q2 = 0ull;
 #pragma unroll
   for (int j = 0; j < DW_TT; ++j) {
     if (j < nvalid) {
-      const float d0 = a0[j] - m0, d1 = a1[j] - m1;
-      q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+      const f32x2 d = add2(acc[j], negm);
+      q2 = fma2(d, d, q2);
     }
   }
+  float q0, q1;
+  unpack2(q2, q0, q1);
   float* part = p.part + (((int64_t)b * gridDim.y + chunk) * p.C + c) * 2;
   *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
 }
