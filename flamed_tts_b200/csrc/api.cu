@@ -136,7 +136,7 @@ struct flm_durgen : Engine {
         gemm(problem(n.c1, n.a0.p, n.D, B, P, P, n.r1.p, n.F, 0, EPI_NONE), n.c1, false, s);
         LnMod ln;
         memset(&ln, 0, sizeof(ln));
-        ln.x = n.r1.as<float>(); ln.ldx = n.F; ln.y = n.l1.p; ln.ldy = n.F; ln.y_bf16 = 0;
+        ln.x = n.r1.p; ln.ldx = n.F; ln.y = n.l1.p; ln.ldy = n.F; ln.y_bf16 = 0;
         ln.w = n.ln1w; ln.b = n.ln1b; ln.eps = 1e-5f; ln.rows = rows; ln.rows_per_batch = P; ln.C = n.F;
         ln.relu_in = 1;
         launch_ln_mod(ln, s);
@@ -251,6 +251,8 @@ struct ResBlockW {
 struct flm_denoiser : Engine {
   flm_prob_cfg cfg;
   int H, D, ada_n;
+  bool h16 = false;  // bf16 residual stream inside a step (FLM_BF16 mode, opt-in: FLAMED_B200_RESIDUAL=bf16)
+  size_t hsize() const { return h16 ? 2 : 4; }
   // denoiser weights
   Layer time0, time2, cond_embed, proj_in, ada_all, conv_out;
   std::vector<ResBlockW> blocks;
@@ -358,7 +360,7 @@ struct flm_denoiser : Engine {
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
     p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
-    p.hres = h.as<float>(); p.ld_res = H;
+    p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
     gemm(p, c.conv3, bf(), s);
   }
 
@@ -366,10 +368,10 @@ struct flm_denoiser : Engine {
                    cudaStream_t s) {
     LnMod ln;
     memset(&ln, 0, sizeof(ln));
-    ln.x = h.as<float>(); ln.ldx = H; ln.y = y; ln.ldy = H; ln.y_bf16 = bf() ? 1 : 0;
+    ln.x = h.p; ln.ldx = H; ln.x_bf16 = h16 ? 1 : 0; ln.y = y; ln.ldy = H; ln.y_bf16 = bf() ? 1 : 0;
     ln.w = w; ln.b = b; ln.shift = shift; ln.scale = scale; ln.mod_bstride = ada_n; ln.scale_plus_one = 1.f;
     ln.eps = 1e-6f; ln.rows = (int64_t)B * L; ln.rows_per_batch = L; ln.C = H;
-    ProfScope ps(ctx, KC_LN_MOD, s, (double)B * L * H * 8, (double)B * L * H * (4 + esize()));
+    ProfScope ps(ctx, KC_LN_MOD, s, (double)B * L * H * 8, (double)B * L * H * (hsize() + esize()));
     launch_ln_mod(ln, s);
   }
 
@@ -389,7 +391,7 @@ struct flm_denoiser : Engine {
     const float* xin = x.as<float>();
     if (bf()) {
       launch_f32_to_bf16(xin, xb.as<bf16>(), M * D, s);
-      gemm(problem(proj_in, xb.p, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, true, s);
+      gemm(problem(proj_in, xb.p, D, B, L, L, h.p, H, h16 ? 1 : 0, EPI_NONE), proj_in, true, s);
     } else {
       gemm(problem(proj_in, xin, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, false, s);
     }
@@ -403,7 +405,7 @@ struct flm_denoiser : Engine {
       ln_modulate(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
       gemm(problem(rb.mlp0, bufU.p, H, B, L, L, bufA.p, H, b16, EPI_SILU), rb.mlp0, bf(), s);
       TapGemm p = problem(rb.mlp2, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
-      p.gate = a + 5 * H; p.gate_bstride = ada_n; p.hres = h.as<float>(); p.ld_res = H;
+      p.gate = a + 5 * H; p.gate_bstride = ada_n; p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
       gemm(p, rb.mlp2, bf(), s);
     }
     const float* a = arow + blocks.size() * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m
@@ -447,6 +449,10 @@ extern "C" int flm_denoiser_load(flm_ctx* ctx, const flm_tensor* weights, int n,
   WeightMap wm(weights, n);
   std::unique_ptr<flm_denoiser> h(new flm_denoiser(ctx, mode));
   h->cfg = *cfg;
+  {
+    const char* r = getenv("FLAMED_B200_RESIDUAL");
+    h->h16 = mode == FLM_BF16 && r && std::string(r) == "bf16";  // default: fp32 stream (accuracy)
+  }
   h->load(wm);
   *out = h.release();
   FLM_API_END
@@ -939,6 +945,7 @@ extern "C" int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, in
   p.K = K; p.N = N; p.ntaps = ntaps; p.off0 = -(ntaps / 2) * dil; p.dil = dil; p.stride = 1; p.epi = epi;
   p.out_bf16 = out_bf16;
   p.gate = g.as<float>(); p.gate_bstride = N; p.hres = h.as<float>(); p.ld_res = N;
+  if (epi == EPI_RESID) { p.resid_in = o.p; }
   cudaEvent_t e0, e1;
   FLM_CUDA(cudaEventCreate(&e0));
   FLM_CUDA(cudaEventCreate(&e1));

@@ -159,8 +159,9 @@ struct TapGemm {
   const void* addend;    // (B,T_out,N) storage type = A's, row stride ld_add (inner ConvNeXt residual u)
   int64_t ld_add;
   int addend_bf16;
-  float* hres;           // fp32 residual stream (B,T_out,N), row stride ld_res, updated in place
-  int64_t ld_res;
+  float* hres;           // residual stream (B,T_out,N), row stride ld_res, updated in place: fp32, or bf16 when
+  int64_t ld_res;        //   hres_bf16 != 0 (EPI_GATE_RESID on the tcgen05 path only; EPI_EULER is always fp32)
+  int hres_bf16;
   const void* resid_in;  // EPI_RESID: (B,T_out,N) same storage type as out, row stride ldc
   float alpha;
 };

@@ -226,7 +226,7 @@ struct Engine {
     const double M = (double)p.B * p.T_out;
     const double flops = 2.0 * M * p.N * p.K * p.ntaps * l.alg_scale;
     const double bytes = M * p.K * (a_bf16 ? 2 : 4) + (double)p.ntaps * p.N * p.K * (a_bf16 ? 2 : 4) +
-                         M * p.N * ((p.epi == EPI_GATE_RESID || p.epi == EPI_EULER) ? 8 : (p.out_bf16 ? 2 : 4));
+                         M * p.N * ((p.epi == EPI_GATE_RESID || p.epi == EPI_EULER) ? (p.hres_bf16 ? 4 : 8) : (p.out_bf16 ? 2 : 4));
     ProfScope ps(ctx, a_bf16 ? KC_GEMM_TC : KC_GEMM_FMA, s, flops, bytes);
     if (a_bf16) {
       if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");

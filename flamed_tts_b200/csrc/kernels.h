@@ -19,7 +19,7 @@ void kernels_norm_init();
 // ---- row-wise LayerNorm (+ adaLN modulate): one warp per row, C % 128 == 0, C <= 1024
 // y = LN(x; w, b, eps) * (scale_plus_one + scale[bi]) + shift[bi],  bi = row / rows_per_batch
 struct LnMod {
-  const float* x; int64_t ldx;  // fp32 input rows
+  const void* x; int64_t ldx; int x_bf16;  // input rows (fp32, or bf16 when x_bf16)
   void* y; int64_t ldy; int y_bf16;
   const float* w; const float* b;  // affine (nullable)
   const float* shift; const float* scale; int64_t mod_bstride;  // per-sample modulation (nullable)

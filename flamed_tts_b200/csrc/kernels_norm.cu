@@ -26,13 +26,13 @@ constexpr int LN_WARPS = 16;
 
 __device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int NV>
+template <int NV, typename TI>
 __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64_t rows_per_warp) {
   constexpr int C = NV * 128;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* ring = reinterpret_cast<float*>(ln_smem) + (size_t)warp * LN_DEPTH * C;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)LN_WARPS * LN_DEPTH * C * 4) + warp * LN_DEPTH;
+  TI* ring = reinterpret_cast<TI*>(ln_smem) + (size_t)warp * LN_DEPTH * C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)LN_WARPS * LN_DEPTH * C * sizeof(TI)) + warp * LN_DEPTH;
   const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp;
   const int64_t r_begin = gw * rows_per_warp;
   const int64_t r_end = min(p.rows, r_begin + rows_per_warp);
@@ -46,10 +46,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
   __syncwarp();
   auto issue = [&](int64_t r, int slot) {  // lane 0 only
     const uint32_t bar = ln_smem_u32(&bars[slot]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * 4)) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * sizeof(TI)))
+                 : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      ln_smem_u32(ring + (size_t)slot * C)),
-                 "l"(p.x + r * p.ldx), "r"((uint32_t)(C * 4)), "r"(bar)
+                 "l"(static_cast<const TI*>(p.x) + r * p.ldx), "r"((uint32_t)(C * sizeof(TI))), "r"(bar)
                  : "memory");
   };
   if (lane == 0) {
@@ -74,9 +75,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
       } while (!done);
     }
     float v[NV][4];
-    const float* xs = ring + (size_t)slot * C;
+    const TI* xs = ring + (size_t)slot * C;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) ld4<float>(xs + (i * 32 + lane) * 4, v[i]);
+    for (int i = 0; i < NV; ++i) ld4<TI>(xs + (i * 32 + lane) * 4, v[i]);
     __syncwarp();
     if (lane == 0 && row + LN_DEPTH < r_end) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
@@ -140,28 +141,33 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
   }
 }
 
-template <int NV>
-constexpr int ln_smem_bytes() { return LN_WARPS * LN_DEPTH * NV * 128 * 4 + LN_WARPS * LN_DEPTH * 8; }
+template <int NV, typename TI>
+constexpr int ln_smem_bytes() { return LN_WARPS * LN_DEPTH * NV * 128 * (int)sizeof(TI) + LN_WARPS * LN_DEPTH * 8; }
 template <int NV>
 void ln_set_attr() {
-  FLM_CUDA(cudaFuncSetAttribute(ln_mod_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln_smem_bytes<NV>()));
+  FLM_CUDA(cudaFuncSetAttribute(ln_mod_kernel<NV, float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ln_smem_bytes<NV, float>()));
+  FLM_CUDA(cudaFuncSetAttribute(ln_mod_kernel<NV, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ln_smem_bytes<NV, bf16>()));
 }
 
 template <int NV>
 void ln_launch(const LnMod& p, int sms, cudaStream_t stream) {
-  constexpr int smem = ln_smem_bytes<NV>();
   int64_t blocks = (p.rows + LN_WARPS - 1) / LN_WARPS;
   if (blocks > sms) blocks = sms;
   const int64_t total_warps = blocks * LN_WARPS;
   const int64_t rpw = (p.rows + total_warps - 1) / total_warps;
-  ln_mod_kernel<NV><<<(unsigned)blocks, LN_WARPS * 32, smem, stream>>>(p, rpw);
+  if (p.x_bf16)
+    ln_mod_kernel<NV, bf16><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, bf16>(), stream>>>(p, rpw);
+  else
+    ln_mod_kernel<NV, float><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, float>(), stream>>>(p, rpw);
 }
 
 }  // namespace
 
 void launch_ln_mod(const LnMod& p, cudaStream_t stream) {
   FLM_REQUIRE(p.C % 128 == 0 && p.C <= 128 * LN_MAX_V, "ln_mod: C must be a multiple of 128 and <= 1024");
-  FLM_REQUIRE(p.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0, "ln_mod: input rows must be 16-byte aligned");
+  FLM_REQUIRE(p.ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0, "ln_mod: input rows must be 16-byte aligned");
   if (p.rows == 0) return;
   static int sms = 0;
   if (!sms) {

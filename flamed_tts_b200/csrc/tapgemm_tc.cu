@@ -158,30 +158,35 @@ __device__ __forceinline__ void warp_rows(const TapGemm& p, const Sched& sch, in
   }
 }
 
-// pull the residual-stream / addend segments a warp will read in the epilogue of `tile` into L2 while the
-// tensor core is still busy with it (lane = row, one 128 B line per 32-column chunk)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// pull the residual-stream / addend rows the epilogue of `tile` will read into L2 while the tensor core is
+// still busy with it: lane = row, one bulk prefetch per row covering all BLOCK_N columns of the tile
+// (issued by the half-0 warp of each TMEM lane quarter)
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void prefetch_epilogue_operands(const TapGemm& p, const Sched& sch, int tile, int quarter,
                                                            int half, int lane) {
+  if (half != 0) return;
   const int nt = tile % sch.num_n_tiles, mt = tile / sch.num_n_tiles;
   int64_t m_w;
   int b_w, t_w, rows_valid;
   warp_rows(p, sch, mt, quarter, m_w, b_w, t_w, rows_valid);
   if (lane >= rows_valid) return;
   const int64_t m = m_w + lane;
-#pragma unroll
-  for (int ch = half; ch < BLOCK_N / 32; ch += 2) {
-    const int n = nt * BLOCK_N + ch * 32;
-    if (EPI == EPI_RESID) {
-      if (p.out_bf16) prefetch_l2(static_cast<const bf16*>(p.resid_in) + m * p.ldc + n);
-      else prefetch_l2(static_cast<const float*>(p.resid_in) + m * p.ldc + n);
-    } else {
-      prefetch_l2(p.hres + m * p.ld_res + n);
-    }
-    if (EPI == EPI_GATE_RESID && p.addend) {
-      if (p.addend_bf16) prefetch_l2(static_cast<const bf16*>(p.addend) + m * p.ld_add + n);
-      else prefetch_l2(static_cast<const float*>(p.addend) + m * p.ld_add + n);
-    }
+  const int n = nt * BLOCK_N;
+  if (EPI == EPI_RESID) {
+    if (p.out_bf16) prefetch_l2_bulk(static_cast<const bf16*>(p.resid_in) + m * p.ldc + n, BLOCK_N * 2);
+    else prefetch_l2_bulk(static_cast<const float*>(p.resid_in) + m * p.ldc + n, BLOCK_N * 4);
+  } else if (EPI == EPI_GATE_RESID && p.hres_bf16) {
+    prefetch_l2_bulk(reinterpret_cast<const bf16*>(p.hres) + m * p.ld_res + n, BLOCK_N * 2);
+  } else {
+    prefetch_l2_bulk(p.hres + m * p.ld_res + n, BLOCK_N * 4);
+  }
+  if (EPI == EPI_GATE_RESID && p.addend) {
+    if (p.addend_bf16) prefetch_l2_bulk(static_cast<const bf16*>(p.addend) + m * p.ld_add + n, BLOCK_N * 2);
+    else prefetch_l2_bulk(static_cast<const float*>(p.addend) + m * p.ld_add + n, BLOCK_N * 4);
   }
 }
 
@@ -317,7 +322,7 @@ __device__ __forceinline__ void epilogue_transposed(const TapGemm& p, float (&v)
   const int col = n + lane;
   const float bias = p.bias ? __ldg(p.bias + col) : 0.f;
   const bool full = rows_valid == 32 && t0 + 32 <= p.T_out;
-  const bool res_bf16 = EPI == EPI_RESID && p.out_bf16;
+  const bool res_bf16 = (EPI == EPI_RESID && p.out_bf16) || (EPI == EPI_GATE_RESID && p.hres_bf16);
   const bool add_bf16 = EPI == EPI_GATE_RESID && p.addend_bf16 != 0;
   if (res_bf16) {
     if (full) epilogue_rows<EPI, true, bf16, bf16>(p, stage, lane, m_base, rows_valid, b0, t0, col, bias);

@@ -24,6 +24,10 @@ cases = [  # mode, B, T, K, N, ntaps, dil, epi, out_bf16
     (1, 64, 120000, 64, 64, 7, 1, 0, 1),
     (1, 1, 350, 1024, 1024, 1, 1, 1, 1),
     (0, 1, 8192, 1024, 1024, 1, 1, 1, 0),
+    (1, 1, 76800, 1024, 1024, 1, 1, 0, 0),   # 10: plain, fp32 out (direct path, 4 B/elt store)
+    (1, 1, 76800, 1024, 1024, 1, 1, 4, 1),   # 11: codec-style skip, bf16 in place (transposed path, 2+2 B/elt)
+    (1, 1, 76800, 1024, 1024, 1, 1, 4, 0),   # 12: skip, fp32 in place (transposed path, 4+4 B/elt)
+    (1, 1, 76800, 1024, 1024, 1, 1, 2, 1),   # 13: SiLU bf16
 ]
 if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
