@@ -56,6 +56,7 @@ SIGNATURES = {
     "flm_profile_enable": (c_int, [c_void_p, c_int]),
     "flm_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), c_int]),
     "flm_profile_class_name": (c_char_p, [c_int]),
+    "flm_profile_detail": (c_int, [c_void_p, c_char_p, c_int]),
     "flm_tapgemm_test": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "flm_tapgemm_bench": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

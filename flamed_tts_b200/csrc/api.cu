@@ -857,6 +857,7 @@ extern "C" int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64
 }
 
 // ===================================================================================== profiler
+extern "C" const char* flm_profile_class_name(int kc);
 extern "C" int flm_profile_enable(flm_ctx* ctx, int on) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx != nullptr, "null ctx");
@@ -882,6 +883,32 @@ extern "C" int flm_profile_read(flm_ctx* ctx, double* out, int n_classes) {
     out[r.kc * 4 + 2] += r.flops;
     out[r.kc * 4 + 3] += r.bytes;
   }
+  FLM_API_END
+}
+
+// per-shape detail of the same records: one text line per (class, tag): "class|tag|launches|ms|flops|bytes"
+extern "C" int flm_profile_detail(flm_ctx* ctx, char* out, int cap) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && out && cap > 0, "bad arguments");
+  set_device(ctx);
+  FLM_CUDA(cudaDeviceSynchronize());
+  struct Agg { double n = 0, ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : ctx->recs) {
+    float ms = 0.f;
+    FLM_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    Agg& a = agg[std::string(flm_profile_class_name(r.kc)) + "|" + r.tag];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  std::string s;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s|%.0f|%.4f|%.6e|%.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops,
+             kv.second.bytes);
+    s += line;
+  }
+  if ((int)s.size() + 1 > cap) throw Error(FLM_ERR_ARG, "flm_profile_detail: buffer too small");
+  memcpy(out, s.c_str(), s.size() + 1);
   FLM_API_END
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -36,7 +37,7 @@ struct flm_ctx {
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled
   // profiler state
   bool prof_on = false;
-  struct Rec { int kc; cudaEvent_t a, b; double flops, bytes; };
+  struct Rec { int kc; cudaEvent_t a, b; double flops, bytes; std::string tag; };
   std::vector<Rec> recs;
   std::vector<cudaEvent_t> pool;
   cudaEvent_t get_event() {
@@ -57,12 +58,14 @@ namespace flm {
 // never while the stream is being captured into a graph)
 struct ProfScope {
   flm_ctx* c; cudaStream_t s; cudaEvent_t b = nullptr;
-  ProfScope(flm_ctx* ctx, int kc, cudaStream_t st, double flops, double bytes) : c(ctx), s(st) {
+  ProfScope(flm_ctx* ctx, int kc, cudaStream_t st, double flops, double bytes, const char* tag = nullptr)
+      : c(ctx), s(st) {
     if (!c->prof_on) return;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
     flm_ctx::Rec r;
     r.kc = kc; r.a = c->get_event(); r.b = c->get_event(); r.flops = flops; r.bytes = bytes;
+    if (tag) r.tag = tag;
     cudaEventRecord(r.a, s);
     b = r.b;
     c->recs.push_back(r);
@@ -227,7 +230,11 @@ struct Engine {
     const double flops = 2.0 * M * p.N * p.K * p.ntaps * l.alg_scale;
     const double bytes = M * p.K * (a_bf16 ? 2 : 4) + (double)p.ntaps * p.N * p.K * (a_bf16 ? 2 : 4) +
                          M * p.N * ((p.epi == EPI_GATE_RESID || p.epi == EPI_EULER) ? (p.hres_bf16 ? 4 : 8) : (p.out_bf16 ? 2 : 4));
-    ProfScope ps(ctx, a_bf16 ? KC_GEMM_TC : KC_GEMM_FMA, s, flops, bytes);
+    char tag[96];
+    tag[0] = 0;
+    if (ctx->prof_on)
+      snprintf(tag, sizeof(tag), "K%d N%d taps%d epi%d B%d T%d", p.K, p.N, p.ntaps, p.epi, p.B, p.T_out);
+    ProfScope ps(ctx, a_bf16 ? KC_GEMM_TC : KC_GEMM_FMA, s, flops, bytes, tag);
     if (a_bf16) {
       if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");
       p.W = l.w16;

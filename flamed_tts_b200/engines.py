@@ -65,6 +65,17 @@ class Context:
                 out[self.lib.flm_profile_class_name(k).decode()] = dict(launches=int(cnt), ms=ms, flops=flops, bytes=byts)
         return out
 
+    def profile_detail(self):
+        """same records keyed by (class, shape tag) -> list of dict(cls, tag, launches, ms, flops, bytes)"""
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        check(self.lib.flm_profile_detail(self.handle, buf, cap))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            cls, tag, n, ms, fl, by = line.split("|")
+            rows.append(dict(cls=cls, tag=tag, launches=int(float(n)), ms=float(ms), flops=float(fl), bytes=float(by)))
+        return rows
+
 
 def _f32(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()

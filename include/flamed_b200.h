@@ -148,6 +148,9 @@ int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S, float
 int flm_profile_enable(flm_ctx* ctx, int on);
 int flm_profile_read(flm_ctx* ctx, double* out, int n_classes);
 const char* flm_profile_class_name(int kclass);
+/* per-shape detail of the same records, one text line per (class, tag):
+ * "class|tag|launches|ms|flops|bytes\n" (tag of a tap-GEMM: "K.. N.. taps.. epi.. B.. T..") */
+int flm_profile_detail(flm_ctx* ctx, char* out, int cap);
 
 /* ---------------------------------------------------------------- generic kernels exposed for tests
  * out[b,t,n] = epi(sum_tap sum_k A[b, t*stride + off0 + tap*dil, k] * W[tap][n][k] + bias[n]),
