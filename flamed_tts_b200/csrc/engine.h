@@ -35,6 +35,7 @@ struct flm_ctx {
   int device = 0;
   int num_sms = 0;
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled
+  int gemm_gen = 2;            // 2: CTA-pair kernel (tapgemm_tc2.cu) where it applies; 1: first-generation kernel only
   // profiler state
   bool prof_on = false;
   struct Rec { int kc; cudaEvent_t a, b; double flops, bytes; std::string tag; };
@@ -238,7 +239,8 @@ struct Engine {
     if (a_bf16) {
       if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");
       p.W = l.w16;
-      launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
+      if (ctx->gemm_gen >= 2 && tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, s);
+      else launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
     } else {
       p.W = l.w32;
       launch_tapgemm_simt(p, s);

@@ -14,6 +14,10 @@ void launch_tapgemm_simt(const TapGemm& p, cudaStream_t stream);
 void launch_tapgemm_tc(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream);
 bool tapgemm_tc_supported(const TapGemm& p);
 void tapgemm_tc_init();
+// second generation: CTA pairs (cta_group::2) + TMA epilogue, bf16 outputs / bf16 residual stream only
+void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream);
+bool tapgemm_tc2_supported(const TapGemm& p);
+void tapgemm_tc2_init();
 void kernels_norm_init();
 
 // ---- row-wise LayerNorm (+ adaLN modulate): one warp per row, C % 128 == 0, C <= 1024
@@ -37,6 +41,11 @@ struct DwConv {
   const float* bias;  // (C)
   float* part;      // (B, nchunk, C, 2) = (mean, M2) of each chunk of DW_TT outputs
   int B, L, C, KW;
+  // optional fused GroupNorm(C,C) finalisation (scale != null): the last block of each (sample, 256-channel
+  // block) merges the partials into scale = gamma*rstd, offset = beta - mean*scale, both (B, C)
+  const float* gamma; const float* beta; float eps;
+  float* scale; float* offset;
+  int* counters;    // (B, C/256) arrival tickets, zero before the first launch, re-armed by the kernel
 };
 constexpr int DW_TT = 32;
 inline int dw_nchunk(int L) { return (L + DW_TT - 1) / DW_TT; }
@@ -57,6 +66,10 @@ void launch_gn_finalize(const float* part, int B, int L, int C, int G, int nchun
 // ---- ConvNeXt GroupNorm(C,C): merge of the depthwise kernel's partials fused with the affine apply
 void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, const float* gamma, const float* beta,
                         float eps, int B, int L, int C, int nchunk, int chunk_rows, cudaStream_t stream);
+
+// ---- y = x*scale[b,c] + offset[b,c], streaming (ConvNeXt GroupNorm apply after the fused finalisation)
+void launch_gn_stream(const void* x, void* y, int io_bf16, const float* scale, const float* offset, int B, int L, int C,
+                      cudaStream_t stream);
 
 // ---- y = act(x*scale[b,c] + offset[b,c]) (*mask[b,t]) (+ res)   act: 0 none, 1 relu, 2 mish
 struct GnApply {

@@ -307,6 +307,121 @@ __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   unpack2(q2, q0, q1);
   float* part = p.part + (((int64_t)b * gridDim.y + chunk) * p.C + c) * 2;
   *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
+  if (p.scale == nullptr) return;
+  // GroupNorm(C,C) statistics: the last block of (sample b, channel block) to finish merges the chunk
+  // partials in a fixed order (deterministic, no float atomics) into scale = gamma*rstd, offset = beta - mean*scale
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* ctr = p.counters + b * gridDim.x + blockIdx.x;
+    const int old = atomicAdd(ctr, 1);
+    is_last = old == (int)gridDim.y - 1;
+    if (is_last) *ctr = 0;  // re-armed for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // two passes over the partials, no divisions: mean = sum(n_k m_k)/N; M2 = sum(q_k + n_k (m_k - mean)^2)
+  const int nchunk = gridDim.y;
+  const float* pbase = p.part + ((int64_t)b * nchunk * p.C + c) * 2;
+  double sm0 = 0.0, sm1 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
+    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
+    sm0 += nb * pk.x; sm1 += nb * pk.z;
+  }
+  const double inv_n = 1.0 / (double)p.L;
+  const double mean0 = sm0 * inv_n, mean1 = sm1 * inv_n;
+  double v0 = 0.0, v1 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
+    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
+    const double d0 = pk.x - mean0, d1 = pk.z - mean1;
+    v0 += pk.y + nb * d0 * d0; v1 += pk.w + nb * d1 * d1;
+  }
+  const float2 ga = *reinterpret_cast<const float2*>(p.gamma + c);
+  const float2 be = *reinterpret_cast<const float2*>(p.beta + c);
+  const float sc0 = ga.x * rsqrtf((float)(v0 * inv_n) + p.eps);
+  const float sc1 = ga.y * rsqrtf((float)(v1 * inv_n) + p.eps);
+  *reinterpret_cast<float2*>(p.scale + (int64_t)b * p.C + c) = make_float2(sc0, sc1);
+  *reinterpret_cast<float2*>(p.offset + (int64_t)b * p.C + c) = make_float2(be.x - (float)mean0 * sc0, be.y - (float)mean1 * sc1);
+}
+
+// y[b,t,c] = x[b,t,c]*scale[b,c] + offset[b,c]: pure streaming pass, 16-byte vectors, the per-sample
+// coefficients of a thread's channels held in registers.  block = (GNS_ROWS rows of sample b), 8 B200-sized
+// row groups per block so that >= 8 independent 16 B loads per thread are in flight.
+constexpr int GNS_ROWS = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stream_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ offset, int L, int C) {
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte vector
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * GNS_ROWS;
+  const int nrows = min(GNS_ROWS, L - r0);
+  const int vpr = C / V;                    // vectors per row
+  const int rstep = 256 / vpr;              // rows covered by one sweep of the block (C=1024: 2 bf16 / 1 fp32)
+  const int col = (threadIdx.x % vpr) * V;
+  const int rsub = threadIdx.x / vpr;
+  if (rsub >= rstep) return;
+  float sc[V], of[V];
+#pragma unroll
+  for (int j = 0; j < V; j += 4) {
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)b * C + col + j));
+    const float4 o4 = __ldg(reinterpret_cast<const float4*>(offset + (int64_t)b * C + col + j));
+    sc[j] = s4.x; sc[j + 1] = s4.y; sc[j + 2] = s4.z; sc[j + 3] = s4.w;
+    of[j] = o4.x; of[j + 1] = o4.y; of[j + 2] = o4.z; of[j + 3] = o4.w;
+  }
+  const T* xp = x + ((int64_t)b * L + r0 + rsub) * C + col;
+  T* yp = y + ((int64_t)b * L + r0 + rsub) * C + col;
+  constexpr int U = 8;
+  int r = rsub;
+  for (; r + (U - 1) * rstep < nrows; r += U * rstep) {
+    uint4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = __ldcs(reinterpret_cast<const uint4*>(xp + (int64_t)u * rstep * C));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (sizeof(T) == 2) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(&q[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a0 = fmaf(__uint_as_float(w[j] << 16), sc[2 * j], of[2 * j]);
+          const float a1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), sc[2 * j + 1], of[2 * j + 1]);
+          __nv_bfloat162 o = __floats2bfloat162_rn(a0, a1);
+          w[j] = *reinterpret_cast<uint32_t*>(&o);
+        }
+      } else {
+        float* w = reinterpret_cast<float*>(&q[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = fmaf(w[j], sc[j], of[j]);
+      }
+      *reinterpret_cast<uint4*>(yp + (int64_t)u * rstep * C) = q[u];
+    }
+    xp += (int64_t)U * rstep * C;
+    yp += (int64_t)U * rstep * C;
+  }
+  for (; r < nrows; r += rstep) {
+    uint4 q = *reinterpret_cast<const uint4*>(xp);
+    if (sizeof(T) == 2) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = fmaf(__uint_as_float(w[j] << 16), sc[2 * j], of[2 * j]);
+        const float a1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), sc[2 * j + 1], of[2 * j + 1]);
+        __nv_bfloat162 o = __floats2bfloat162_rn(a0, a1);
+        w[j] = *reinterpret_cast<uint32_t*>(&o);
+      }
+    } else {
+      float* w = reinterpret_cast<float*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = fmaf(w[j], sc[j], of[j]);
+    }
+    *reinterpret_cast<uint4*>(yp) = q;
+    xp += (int64_t)rstep * C;
+    yp += (int64_t)rstep * C;
+  }
 }
 
 }  // namespace
@@ -494,6 +609,19 @@ void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, 
   else
     gn_convnext_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), part,
                                                         gamma, beta, eps, L, C, nchunk, chunk_rows);
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_gn_stream(const void* x, void* y, int io_bf16, const float* scale, const float* offset, int B, int L, int C,
+                      cudaStream_t stream) {
+  const int V = io_bf16 ? 8 : 4;
+  FLM_REQUIRE(C % V == 0 && C / V <= 256 && 256 % (C / V) == 0, "gn_stream: unsupported channel count");
+  if (B == 0 || L == 0) return;
+  dim3 grid((L + GNS_ROWS - 1) / GNS_ROWS, B);
+  if (io_bf16)
+    gn_stream_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), scale, offset, L, C);
+  else
+    gn_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), scale, offset, L, C);
   FLM_LAUNCH_CHECK();
 }
 

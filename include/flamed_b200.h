@@ -161,6 +161,14 @@ int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, con
                      int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi, float* out,
                      flm_stream stream);
 
+/* bf16-in / bf16-out form of the same problem on the tcgen05 kernels: gen 1 = single-CTA kernel, 2 = CTA-pair
+ * (cta_group::2) kernel with the TMA epilogue.  A, W, out, resid, addend are device bf16; bias (N) and gate (B,N)
+ * are f32.  epi 0..3 as above; 4: out = resid + v (codec skip connection, facodec.py:131-133);
+ * 5: resid += gate[b,:] * (v + addend) in place (adaLN-gated residual, prob_generator.py:162-163; addend nullable). */
+int flm_tapgemm_test_bf16(flm_ctx* ctx, int gen, const void* A, const void* W, const float* bias, int B, int T_in,
+                          int T_out, int K, int N, int ntaps, int off0, int dil, int epi, void* out, void* resid,
+                          const void* addend, const float* gate, flm_stream stream);
+
 /* micro-benchmark hook: `reps` launches of one tap-GEMM (pseudo-random operands) timed with CUDA events on
  * `stream`; *out_ms = average ms per launch.  A (B,T,K), W (ntaps,N,K); epi 0..3 or 5 (gated residual). */
 int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, int N, int ntaps, int dil, int epi, int out_bf16,
