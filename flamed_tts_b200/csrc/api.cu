@@ -352,6 +352,7 @@ struct flm_denoiser : Engine {
     dw.B = B; dw.L = L; dw.C = H; dw.KW = cfg.kernel_size;
     dw.gamma = c.gn_w; dw.beta = c.gn_b; dw.eps = 1e-5f; dw.scale = gsc.as<float>(); dw.offset = gof.as<float>();
     dw.counters = gctr.as<int>();
+    dw.tma_encode = dw_persistent() ? ctx->tma_encode : nullptr;
     const double elems = (double)B * L * H, eb = (double)esize();
     {
       ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * cfg.kernel_size, elems * 2 * eb);
@@ -420,7 +421,11 @@ struct flm_denoiser : Engine {
     p.hres = target; p.ld_res = D; p.alpha = alpha;
     gemm(p, conv_out, bf(), s);
   }
-  int launches_per_step() const { return (bf() ? 2 : 1) + (int)blocks.size() * 8 + 7; }
+  // the persistent depthwise kernel (bf16 mode) is followed by its statistics-merge kernel: +1 per ConvNeXt
+  bool dw_persistent() const { return bf() && !getenv("FLAMED_B200_DWCONV_V1"); }
+  int launches_per_step() const {
+    return (bf() ? 2 : 1) + (int)blocks.size() * 8 + 7 + (dw_persistent() ? (int)blocks.size() + 1 : 0);
+  }
 
   bool ensure(int B, int L, int nfe) {
     const int64_t M = (int64_t)B * L;

@@ -46,6 +46,7 @@ struct DwConv {
   const float* gamma; const float* beta; float eps;
   float* scale; float* offset;
   int* counters;    // (B, C/256) arrival tickets, zero before the first launch, re-armed by the kernel
+  void* tma_encode; // cuTensorMapEncodeTiled entry point: non-null selects the persistent TMA-pipelined kernel (bf16)
 };
 constexpr int DW_TT = 32;
 inline int dw_nchunk(int L) { return (L + DW_TT - 1) / DW_TT; }

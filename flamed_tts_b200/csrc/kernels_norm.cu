@@ -6,6 +6,8 @@
 //   dwconv      <- ConvNeXtBlock.conv_1 (depthwise k=31):      81-88,108-109
 //   gn_finalize <- GroupNorm(C,C) / GroupNorm(8,.) statistics: 89,109; 15-17,187
 //   gn_apply    <- GroupNorm affine (+ Mish/ReLU, mask, skip): 20-22,30-32,198-205
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -230,6 +232,55 @@ __device__ __forceinline__ f32x2 lds_pair<bf16>(const bf16* p) {
   return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
+__device__ __forceinline__ void dw_merge(const DwConv& p, int b, int nchunk, int c);
+
+// GroupNorm(C,C) statistics: the last block of (sample b, 256-channel block) to finish merges the chunk partials
+// in a fixed order (deterministic, no float atomics) into scale = gamma*rstd, offset = beta - mean*scale.
+// Called by all 128 threads of a block after they wrote their partials; c = the thread's first channel.
+__device__ __forceinline__ void dw_finalize(const DwConv& p, int b, int cblk, int chunk, int nchunk, int ncblk, int c) {
+  if (p.scale == nullptr) return;
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int* ctr = p.counters + b * ncblk + cblk;
+    const int old = atomicAdd(ctr, 1);
+    is_last = old == nchunk - 1;
+    if (is_last) *ctr = 0;  // re-armed for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  dw_merge(p, b, nchunk, c);
+}
+
+// merge of the chunk partials of channels (c, c+1) of sample b: two passes, no divisions:
+// mean = sum(n_k m_k)/N; M2 = sum(q_k + n_k (m_k - mean)^2); fixed order -> deterministic
+__device__ __forceinline__ void dw_merge(const DwConv& p, int b, int nchunk, int c) {
+  const float* pbase = p.part + ((int64_t)b * nchunk * p.C + c) * 2;
+  double sm0 = 0.0, sm1 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
+    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
+    sm0 += nb * pk.x; sm1 += nb * pk.z;
+  }
+  const double inv_n = 1.0 / (double)p.L;
+  const double mean0 = sm0 * inv_n, mean1 = sm1 * inv_n;
+  double v0 = 0.0, v1 = 0.0;
+  for (int k = 0; k < nchunk; ++k) {
+    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
+    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
+    const double d0 = pk.x - mean0, d1 = pk.z - mean1;
+    v0 += pk.y + nb * d0 * d0; v1 += pk.w + nb * d1 * d1;
+  }
+  const float2 ga = *reinterpret_cast<const float2*>(p.gamma + c);
+  const float2 be = *reinterpret_cast<const float2*>(p.beta + c);
+  const float sc0 = ga.x * rsqrtf((float)(v0 * inv_n) + p.eps);
+  const float sc1 = ga.y * rsqrtf((float)(v1 * inv_n) + p.eps);
+  *reinterpret_cast<float2*>(p.scale + (int64_t)b * p.C + c) = make_float2(sc0, sc1);
+  *reinterpret_cast<float2*>(p.offset + (int64_t)b * p.C + c) = make_float2(be.x - (float)mean0 * sc0, be.y - (float)mean1 * sc1);
+}
+
 template <typename T, int KW>
 __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   constexpr int PAD = KW / 2;
@@ -307,45 +358,132 @@ __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   unpack2(q2, q0, q1);
   float* part = p.part + (((int64_t)b * gridDim.y + chunk) * p.C + c) * 2;
   *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
-  if (p.scale == nullptr) return;
-  // GroupNorm(C,C) statistics: the last block of (sample b, channel block) to finish merges the chunk
-  // partials in a fixed order (deterministic, no float atomics) into scale = gamma*rstd, offset = beta - mean*scale
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
+  dw_finalize(p, b, blockIdx.x, chunk, gridDim.y, gridDim.x, c);
+}
+
+// Persistent, TMA-pipelined form of the same computation for bf16 storage (the throughput mode): one block
+// streams (sample, chunk) tiles of a FIXED 256-channel block through a DWP_STAGES-deep shared-memory ring.
+// Each tile is one 3-D bulk tensor copy (256 channels x 62 frames, out-of-range frames zero-filled by the TMA
+// unit = the conv's zero padding), issued DWP_STAGES-1 tiles ahead by thread 0, so ~2-3 tiles (60-90 KB) per
+// block are in flight while the 31-tap FFMA2 window runs; the tap weights stay in registers for the whole
+// kernel because the grid is a multiple of the number of channel blocks.
+constexpr int DWP_STAGES = 3;
+template <int KW>
+__global__ void __launch_bounds__(128) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, DwConv p, int nchunk,
+                                                         int ncblk, int ntiles) {
+  constexpr int PAD = KW / 2;
+  constexpr int ROWS = DW_TT + KW - 1;
+  constexpr int TILE_BYTES = ROWS * 256 * 2;
+  extern __shared__ __align__(128) uint8_t dwp_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dwp_smem + DWP_STAGES * TILE_BYTES);
+  const int cblk = blockIdx.x % ncblk;  // gridDim.x % ncblk == 0: constant for every tile of this block
+  const int c = cblk * 256 + threadIdx.x * 2;
   if (threadIdx.x == 0) {
-    int* ctr = p.counters + b * gridDim.x + blockIdx.x;
-    const int old = atomicAdd(ctr, 1);
-    is_last = old == (int)gridDim.y - 1;
-    if (is_last) *ctr = 0;  // re-armed for the next launch
+    for (int i = 0; i < DWP_STAGES; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(&bars[i])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // two passes over the partials, no divisions: mean = sum(n_k m_k)/N; M2 = sum(q_k + n_k (m_k - mean)^2)
-  const int nchunk = gridDim.y;
-  const float* pbase = p.part + ((int64_t)b * nchunk * p.C + c) * 2;
-  double sm0 = 0.0, sm1 = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
-    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
-    sm0 += nb * pk.x; sm1 += nb * pk.z;
+  // work item w of this block: tile id (b * nchunk + chunk) = blockIdx.x / ncblk + w * (gridDim.x / ncblk)
+  const int tstride = gridDim.x / ncblk;
+  const int tfirst = blockIdx.x / ncblk;
+  auto issue = [&](int tile, int slot) {  // thread 0 only
+    const int b = tile / nchunk, chunk = tile % nchunk;
+    const uint32_t bar = ln_smem_u32(&bars[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TILE_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(ln_smem_u32(dwp_smem + slot * TILE_BYTES)),
+        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(cblk * 256), "r"(chunk * DW_TT - PAD), "r"(b)
+        : "memory");
+  };
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < DWP_STAGES - 1; ++d)
+      if (tfirst + d * tstride < ntiles) issue(tfirst + d * tstride, d);
   }
-  const double inv_n = 1.0 / (double)p.L;
-  const double mean0 = sm0 * inv_n, mean1 = sm1 * inv_n;
-  double v0 = 0.0, v1 = 0.0;
-  for (int k = 0; k < nchunk; ++k) {
-    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
-    const double nb = (double)min(DW_TT, p.L - k * DW_TT);
-    const double d0 = pk.x - mean0, d1 = pk.z - mean1;
-    v0 += pk.y + nb * d0 * d0; v1 += pk.w + nb * d1 * d1;
+  f32x2 w2[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) w2[k] = *reinterpret_cast<const f32x2*>(p.w + (int64_t)k * p.C + c);
+  const f32x2 bias2 = *reinterpret_cast<const f32x2*>(p.bias + c);
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int tile = tfirst; tile < ntiles; tile += tstride) {
+    // refill the slot that was drained in the previous iteration (all threads passed its __syncthreads)
+    if (threadIdx.x == 0) {
+      const int nxt = tile + (DWP_STAGES - 1) * tstride;
+      if (nxt < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(nxt, (slot + DWP_STAGES - 1) % DWP_STAGES);
+      }
+    }
+    {
+      const uint32_t bar = ln_smem_u32(&bars[slot]);
+      uint32_t done;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(phase)
+            : "memory");
+      } while (!done);
+    }
+    const bf16* xs = reinterpret_cast<const bf16*>(dwp_smem + slot * TILE_BYTES) + threadIdx.x * 2;
+    f32x2 acc[DW_TT];
+#pragma unroll
+    for (int j = 0; j < DW_TT; ++j) acc[j] = 0ull;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const f32x2 x2 = lds_pair<bf16>(xs + r * 256);
+#pragma unroll
+      for (int j = 0; j < DW_TT; ++j) {
+        const int tap = r - j;  // compile-time after unrolling
+        if (tap >= 0 && tap < KW) acc[j] = fma2(w2[tap], x2, acc[j]);
+      }
+    }
+    __syncthreads();  // the slot may be overwritten from here on
+    const int b = tile / nchunk, chunk = tile % nchunk;
+    const int t0 = chunk * DW_TT;
+    const int nvalid = min(DW_TT, p.L - t0);
+    bf16* yb = static_cast<bf16*>(p.y) + ((int64_t)b * p.L + t0) * p.C + c;
+    f32x2 s2 = 0ull;
+#pragma unroll
+    for (int j = 0; j < DW_TT; ++j) {
+      acc[j] = add2(acc[j], bias2);
+      if (j < nvalid) {
+        float a0, a1;
+        unpack2(acc[j], a0, a1);
+        st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
+        s2 = add2(s2, acc[j]);
+      }
+    }
+    float s0, s1;
+    unpack2(s2, s0, s1);
+    const float inv = 1.0f / (float)nvalid;
+    const float m0 = s0 * inv, m1 = s1 * inv;
+    const f32x2 negm = pack2(-m0, -m1);
+    f32x2 q2 = 0ull;
+#pragma unroll
+    for (int j = 0; j < DW_TT; ++j) {
+      if (j < nvalid) {
+        const f32x2 d = add2(acc[j], negm);
+        q2 = fma2(d, d, q2);
+      }
+    }
+    float q0, q1;
+    unpack2(q2, q0, q1);
+    float* part = p.part + (((int64_t)b * nchunk + chunk) * p.C + c) * 2;
+    *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
+    if (++slot == DWP_STAGES) { slot = 0; phase ^= 1; }
   }
-  const float2 ga = *reinterpret_cast<const float2*>(p.gamma + c);
-  const float2 be = *reinterpret_cast<const float2*>(p.beta + c);
-  const float sc0 = ga.x * rsqrtf((float)(v0 * inv_n) + p.eps);
-  const float sc1 = ga.y * rsqrtf((float)(v1 * inv_n) + p.eps);
-  *reinterpret_cast<float2*>(p.scale + (int64_t)b * p.C + c) = make_float2(sc0, sc1);
-  *reinterpret_cast<float2*>(p.offset + (int64_t)b * p.C + c) = make_float2(be.x - (float)mean0 * sc0, be.y - (float)mean1 * sc1);
+}
+
+// statistics merge after the persistent kernel (a per-tile ticket + __threadfence there would stall every tile on
+// its own stores): thread = 2 channels of one sample
+__global__ void __launch_bounds__(128) dw_merge_kernel(DwConv p, int nchunk) {
+  const int idx = blockIdx.x * 128 + threadIdx.x;  // over B * C/2
+  const int half_c = p.C >> 1;
+  if (idx >= p.B * half_c) return;
+  dw_merge(p, idx / half_c, nchunk, (idx % half_c) * 2);
 }
 
 // y[b,t,c] = x[b,t,c]*scale[b,c] + offset[b,c]: pure streaming pass, 16-byte vectors, the per-sample
@@ -430,8 +568,40 @@ void launch_dwconv(const DwConv& p, cudaStream_t stream) {
   FLM_REQUIRE(p.KW == 31, "dwconv: only kernel_size 31 is compiled (configs/prob.yaml convnext.kernel_size)");
   FLM_REQUIRE(p.C % 256 == 0, "dwconv: C must be a multiple of 256");
   if (p.B == 0 || p.L == 0) return;
-  dim3 grid(p.C / 256, dw_nchunk(p.L), p.B);
   constexpr int ROWS = DW_TT + 31 - 1;
+  if (p.io_bf16 && p.tma_encode && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(p.tma_encode);
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)p.C, (cuuint64_t)p.L, (cuuint64_t)p.B};
+    cuuint64_t strides[2] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.C * 2 * (cuuint64_t)p.L};
+    cuuint32_t box[3] = {256, (cuuint32_t)ROWS, 1}, estr[3] = {1, 1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(dwconv x) failed: " + std::to_string((int)r));
+    const int nchunk = dw_nchunk(p.L), ncblk = p.C / 256;
+    const int ntiles = p.B * nchunk;  // (sample, chunk) tiles per channel block
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_cblk = (2 * sms) / ncblk;  // two resident blocks per SM
+    if (per_cblk > ntiles) per_cblk = ntiles;
+    if (per_cblk < 1) per_cblk = 1;
+    dwconv_tma_kernel<31><<<per_cblk * ncblk, 128, DWP_STAGES * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
+    FLM_LAUNCH_CHECK();
+    if (p.scale) {
+      dw_merge_kernel<<<(p.B * (p.C / 2) + 127) / 128, 128, 0, stream>>>(p, nchunk);
+      FLM_LAUNCH_CHECK();
+    }
+    return;
+  }
+  dim3 grid(p.C / 256, dw_nchunk(p.L), p.B);
   if (p.io_bf16)
     dwconv_kernel<bf16, 31><<<grid, 128, ROWS * 256 * 2, stream>>>(p);
   else
@@ -631,6 +801,8 @@ void kernels_norm_init() {
   constexpr int ROWS = DW_TT + 31 - 1;
   FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<float, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 4));
   FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<bf16, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 2));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                DWP_STAGES * ROWS * 256 * 2 + 64));
 }
 
 void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, float* part, cudaStream_t stream) {
