@@ -51,6 +51,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
     throw Error(FLM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   tapgemm_tc_init();
   tapgemm_tc2_init();
+  dwconv_tc_init();
   if (const char* g = getenv("FLAMED_B200_GEMM")) c->gemm_gen = atoi(g) == 1 ? 1 : 2;
   kernels_norm_init();
   *out = c.release();
@@ -356,7 +357,12 @@ struct flm_denoiser : Engine {
     const double elems = (double)B * L * H, eb = (double)esize();
     {
       ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * cfg.kernel_size, elems * 2 * eb);
-      launch_dwconv(dw, s);
+      if (dw_tensor() && dwconv_tc_supported(dw)) {
+        launch_dwconv_tc(dw, ctx->num_sms, s);
+        launch_dw_merge(dw, s);
+      } else {
+        launch_dwconv(dw, s);
+      }
     }
     {
       ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * eb);
@@ -395,7 +401,8 @@ struct flm_denoiser : Engine {
     const int64_t M = (int64_t)B * L;
     const float* xin = x.as<float>();
     if (bf()) {
-      launch_f32_to_bf16(xin, xb.as<bf16>(), M * D, s);
+      // xb = bf16(x): written by the previous step's Euler epilogue when the loop accumulates into x itself
+      if (!xb_fresh) launch_f32_to_bf16(xin, xb.as<bf16>(), M * D, s);
       gemm(problem(proj_in, xb.p, D, B, L, L, h.p, H, h16 ? 1 : 0, EPI_NONE), proj_in, true, s);
     } else {
       gemm(problem(proj_in, xin, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, false, s);
@@ -419,12 +426,22 @@ struct flm_denoiser : Engine {
     ln_modulate(nullptr, nullptr, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
     TapGemm p = problem(conv_out, bufU.p, H, B, L, L, nullptr, D, 0, EPI_EULER);
     p.hres = target; p.ld_res = D; p.alpha = alpha;
+    xb_fresh = bf() && target == x.as<float>();
+    if (xb_fresh) p.out = xb.p;
     gemm(p, conv_out, bf(), s);
   }
+  bool xb_fresh = false;  // xb holds bf16(x) of the current state
   // the persistent depthwise kernel (bf16 mode) is followed by its statistics-merge kernel: +1 per ConvNeXt
   bool dw_persistent() const { return bf() && !getenv("FLAMED_B200_DWCONV_V1"); }
-  int launches_per_step() const {
-    return (bf() ? 2 : 1) + (int)blocks.size() * 8 + 7 + (dw_persistent() ? (int)blocks.size() + 1 : 0);
+  // experimental tensor-core depthwise conv (dwconv_tc.cu), opt-in with FLAMED_B200_DWCONV=tensor: parity-green but
+  // measured 2.2x SLOWER than the FP32-FMA kernel on B200 (0.37 vs 0.17 ms at 79k frames): with N=16 every MMA
+  // re-reads its 4 KB A operand from shared memory, so the kernel is shared-memory-bandwidth bound
+  bool dw_tensor() const {
+    const char* e = getenv("FLAMED_B200_DWCONV");
+    return bf() && e && std::string(e) == "tensor";
+  }
+  int launches_per_step() const {  // steady state (the first step of a loop adds the f32 -> bf16 conversion of x0)
+    return 1 + (int)blocks.size() * 8 + 7 + ((dw_persistent() || dw_tensor()) ? (int)blocks.size() + 1 : 0);
   }
 
   bool ensure(int B, int L, int nfe) {
@@ -541,6 +558,7 @@ extern "C" int flm_denoiser_sample(flm_denoiser* h, const float* cond, const flo
   FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts_host, (size_t)(nfe + 1) * 4, cudaMemcpyHostToDevice, s));
   const float dt = (float)(1.0 / nfe);
   auto body = [&](cudaStream_t cs) {
+    h->xb_fresh = false;
     h->modulation_table(B, nfe, cs);
     launch_noise_init(h->noise_s.as<float>(), h->cond_s.as<float>(), temperature, M * h->D, h->x.as<float>(), cs);
     for (int i = 0; i < nfe; ++i) h->step(B, L, i, h->x.as<float>(), dt, cs);
@@ -571,6 +589,7 @@ extern "C" int flm_denoiser_forward(flm_denoiser* h, const float* x, const float
   FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts, 8, cudaMemcpyHostToDevice, s));
   FLM_CUDA(cudaMemsetAsync(h->vout.p, 0, M * h->D * 4, s));
   h->modulation_table(B, 1, s);
+  h->xb_fresh = false;
   h->step(B, L, 0, h->vout.as<float>(), 1.0f, s);
   FLM_CUDA(cudaMemcpyAsync(out_v, h->vout.p, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
   FLM_API_END

@@ -147,7 +147,8 @@ struct TapGemm {
   const void* A;   // (B, T_in, K) storage type TA, row stride lda elements
   const void* W;   // (ntaps, N, K) storage type TA
   const float* bias;  // (N) or null
-  void* out;       // (B, T_out, N) row stride ldc elements; may be null for GATE_RESID / EULER
+  void* out;       // (B, T_out, N) row stride ldc elements; may be null for GATE_RESID / EULER.  EULER on the tcgen05
+                   // path: if non-null, receives a bf16 copy of the updated state (operand of the next step's proj_in)
   int64_t lda, ldc;
   int B, T_in, T_out, K, N;
   int ntaps, off0, dil, stride;

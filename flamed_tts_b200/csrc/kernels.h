@@ -51,6 +51,12 @@ struct DwConv {
 constexpr int DW_TT = 32;
 inline int dw_nchunk(int L) { return (L + DW_TT - 1) / DW_TT; }
 void launch_dwconv(const DwConv& p, cudaStream_t stream);
+// tensor-core form (dwconv_tc.cu: bf16, k=31, C % 64 == 0): writes y and the chunk partials only; follow with
+// launch_dw_merge to turn the partials into the GroupNorm(C,C) scale / offset
+void launch_dwconv_tc(const DwConv& p, int num_sms, cudaStream_t stream);
+bool dwconv_tc_supported(const DwConv& p);
+void dwconv_tc_init();
+void launch_dw_merge(const DwConv& p, cudaStream_t stream);
 
 // ---- generic grouped statistics over (rows x channels-in-group) for GroupNorm(G) in the cond
 //      down-sampler: partials (B, nchunk, G, 2) from chunks of GS_ROWS rows

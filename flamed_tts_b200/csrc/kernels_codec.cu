@@ -178,6 +178,66 @@ __global__ void __launch_bounds__(256) conv_out_tanh_kernel(const T* x, const fl
   wav[(int64_t)b * T_ + t] = tanhf(acc + bias);
 }
 
+// bf16 form, memory-bound: LPR = C/8 lanes share a frame (16 B = 8 channels each, so a warp reads 32/LPR whole
+// frames per fully coalesced instruction), every lane keeps its 7 x 8 tap weights in registers, forms the 7
+// partial dot products of its frame, the LPR lanes are summed with xor shuffles, and the per-(tap, frame) dots
+// go through shared memory: wav[t] = tanh(bias + sum_tap dot[tap][t + tap - 3]).  block = COT_T frames.
+constexpr int COT_T = 256;
+template <int LPR>
+__global__ void __launch_bounds__(256) conv_out_tanh_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                 float bias, int T_, float* __restrict__ wav) {
+  constexpr int C = LPR * 8;
+  constexpr int ROWS = COT_T + 6;
+  __shared__ float dots[7][ROWS + 2];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * COT_T;
+  const int sub = threadIdx.x % LPR;          // which 8 channels of the frame
+  const int rsub = threadIdx.x / LPR;         // frame slot inside one sweep of the block
+  constexpr int RPS = 256 / LPR;              // frames per sweep
+  float wr[7][8];
+#pragma unroll
+  for (int tap = 0; tap < 7; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[tap][j] = __ldg(w + tap * C + sub * 8 + j);
+  const bf16* xb = x + (int64_t)b * T_ * C + sub * 8;
+  for (int rbase = 0; rbase < ROWS; rbase += RPS) {  // warp-uniform trip count: the shuffles below need all lanes
+    const int r = rbase + rsub;
+    const int t = t0 - 3 + r;
+    float d[7];
+#pragma unroll
+    for (int tap = 0; tap < 7; ++tap) d[tap] = 0.f;
+    if (r < ROWS && t >= 0 && t < T_) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(xb + (int64_t)t * C));
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[2 * j] = __uint_as_float(u[j] << 16);
+        f[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int tap = 0; tap < 7; ++tap)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[tap] = fmaf(f[j], wr[tap][j], d[tap]);
+    }
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1)
+#pragma unroll
+      for (int tap = 0; tap < 7; ++tap) d[tap] += __shfl_xor_sync(0xffffffffu, d[tap], o);
+#pragma unroll
+    for (int tap = 0; tap < 7; ++tap)
+      if ((tap % LPR) == sub && r < ROWS) dots[tap][r] = d[tap];
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t < T_) {
+    float acc = bias;
+#pragma unroll
+    for (int tap = 0; tap < 7; ++tap) acc += dots[tap][threadIdx.x + tap];  // frame t + tap - 3 = slot (t - t0) + tap
+    wav[(int64_t)b * T_ + t] = tanhf(acc);
+  }
+}
+
 // y[b,t,c] = sum_tap w[tap][c] * wav[b,t+tap-3] + bias[c]
 __global__ void conv_in_wav_kernel(const float* wav, const float* w, const float* bias, int64_t T_, int C, float* y) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -239,6 +299,15 @@ void launch_conv_out_tanh(const void* x, int x_bf16, const float* w, float bias,
                           cudaStream_t stream) {
   FLM_REQUIRE(C % 4 == 0 && C <= 128, "conv_out_tanh: C must be a multiple of 4, <= 128");
   if (B == 0 || T == 0) return;
+  if (x_bf16 && (C == 32 || C == 64 || C == 128) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    dim3 g2((T + COT_T - 1) / COT_T, B);
+    const bf16* xp = static_cast<const bf16*>(x);
+    if (C == 32) conv_out_tanh_bf16_kernel<4><<<g2, 256, 0, stream>>>(xp, w, bias, T, wav);
+    else if (C == 64) conv_out_tanh_bf16_kernel<8><<<g2, 256, 0, stream>>>(xp, w, bias, T, wav);
+    else conv_out_tanh_bf16_kernel<16><<<g2, 256, 0, stream>>>(xp, w, bias, T, wav);
+    FLM_LAUNCH_CHECK();
+    return;
+  }
   dim3 grid((T + 255) / 256, B);
   if (x_bf16)
     conv_out_tanh_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), w, bias, T, C, wav);

@@ -486,6 +486,42 @@ __global__ void __launch_bounds__(128) dw_merge_kernel(DwConv p, int nchunk) {
   dw_merge(p, idx / half_c, nchunk, (idx % half_c) * 2);
 }
 
+// bf16-mode form: one warp per (sample, 64 channels); lane = 2 channels, the chunks are split over the 4 warps of
+// a block and combined through shared memory in a fixed order (deterministic); fp32 with the chunk means taken
+// relative to the first chunk's mean, which keeps the second moment free of cancellation at bf16-level accuracy
+__global__ void __launch_bounds__(128) dw_merge_fast_kernel(DwConv p, int nchunk) {
+  __shared__ float red[4][32][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cgroups = p.C >> 6;
+  const int b = blockIdx.x / cgroups, c = (blockIdx.x % cgroups) * 64 + lane * 2;
+  const float* pbase = p.part + ((int64_t)b * nchunk * p.C + c) * 2;
+  const float4 first = __ldcg(reinterpret_cast<const float4*>(pbase));
+  const float r0 = first.x, r1 = first.z;  // reference means
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (int k = w; k < nchunk; k += 4) {
+    const float4 pk = __ldcg(reinterpret_cast<const float4*>(pbase + (int64_t)k * p.C * 2));
+    const float nb = (float)min(DW_TT, p.L - k * DW_TT);
+    const float d0 = pk.x - r0, d1 = pk.z - r1;
+    s0 = fmaf(nb, d0, s0); s1 = fmaf(nb, d1, s1);
+    q0 += fmaf(nb * d0, d0, pk.y); q1 += fmaf(nb * d1, d1, pk.w);
+  }
+  red[w][lane][0] = s0; red[w][lane][1] = s1; red[w][lane][2] = q0; red[w][lane][3] = q1;
+  __syncthreads();
+  if (w != 0) return;
+  s0 = (red[0][lane][0] + red[1][lane][0]) + (red[2][lane][0] + red[3][lane][0]);
+  s1 = (red[0][lane][1] + red[1][lane][1]) + (red[2][lane][1] + red[3][lane][1]);
+  q0 = (red[0][lane][2] + red[1][lane][2]) + (red[2][lane][2] + red[3][lane][2]);
+  q1 = (red[0][lane][3] + red[1][lane][3]) + (red[2][lane][3] + red[3][lane][3]);
+  const float inv_n = 1.0f / (float)p.L;
+  const float dm0 = s0 * inv_n, dm1 = s1 * inv_n;                    // mean - reference
+  const float var0 = fmaxf(q0 * inv_n - dm0 * dm0, 0.f), var1 = fmaxf(q1 * inv_n - dm1 * dm1, 0.f);
+  const float2 ga = *reinterpret_cast<const float2*>(p.gamma + c);
+  const float2 be = *reinterpret_cast<const float2*>(p.beta + c);
+  const float sc0 = ga.x * rsqrtf(var0 + p.eps), sc1 = ga.y * rsqrtf(var1 + p.eps);
+  *reinterpret_cast<float2*>(p.scale + (int64_t)b * p.C + c) = make_float2(sc0, sc1);
+  *reinterpret_cast<float2*>(p.offset + (int64_t)b * p.C + c) = make_float2(be.x - (r0 + dm0) * sc0, be.y - (r1 + dm1) * sc1);
+}
+
 // y[b,t,c] = x[b,t,c]*scale[b,c] + offset[b,c]: pure streaming pass, 16-byte vectors, the per-sample
 // coefficients of a thread's channels held in registers.  block = (GNS_ROWS rows of sample b), 8 B200-sized
 // row groups per block so that >= 8 independent 16 B loads per thread are in flight.
@@ -595,10 +631,7 @@ void launch_dwconv(const DwConv& p, cudaStream_t stream) {
     if (per_cblk < 1) per_cblk = 1;
     dwconv_tma_kernel<31><<<per_cblk * ncblk, 128, DWP_STAGES * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
     FLM_LAUNCH_CHECK();
-    if (p.scale) {
-      dw_merge_kernel<<<(p.B * (p.C / 2) + 127) / 128, 128, 0, stream>>>(p, nchunk);
-      FLM_LAUNCH_CHECK();
-    }
+    launch_dw_merge(p, stream);
     return;
   }
   dim3 grid(p.C / 256, dw_nchunk(p.L), p.B);
@@ -779,6 +812,16 @@ void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, 
   else
     gn_convnext_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), part,
                                                         gamma, beta, eps, L, C, nchunk, chunk_rows);
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_dw_merge(const DwConv& p, cudaStream_t stream) {
+  if (!p.scale || p.B == 0 || p.L == 0) return;
+  const int nchunk = dw_nchunk(p.L);
+  if (p.io_bf16 && p.C % 64 == 0)
+    dw_merge_fast_kernel<<<p.B * (p.C / 64), 128, 0, stream>>>(p, nchunk);
+  else
+    dw_merge_kernel<<<(p.B * (p.C / 2) + 127) / 128, 128, 0, stream>>>(p, nchunk);
   FLM_LAUNCH_CHECK();
 }
 

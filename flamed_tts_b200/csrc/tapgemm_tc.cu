@@ -300,6 +300,8 @@ __device__ __forceinline__ void epilogue_rows(const TapGemm& p, const float* sta
       else if (EPI == EPI_EULER) o = __fadd_rn(hv[r], __fmul_rn(p.alpha, val));
       else o = hv[r] + val;
       stf<TRES>(rdst + r * rld, o);
+      // Euler update: also hand the next step's proj_in GEMM its bf16 operand (p.out, row stride ldc)
+      if (EPI == EPI_EULER && p.out) static_cast<bf16*>(p.out)[(m_base + r) * p.ldc + col] = __float2bfloat16(o);
     }
     if (!FULL && EPI == EPI_GATE_RESID) {  // rows may cross into the next sample: reload the gate there
       if (++t == p.T_out) {
