@@ -60,10 +60,47 @@ class FFTBlock(nn.Module):
         super().__init__()
         self.slf_attn = _SelfAttention(d_model, n_head)
         self.pos_ffn = _ConvFFN(d_model, d_inner, kernel_size)
+        self._packed = None
 
     def forward(self, x, pad_mask):
         x = self.slf_attn(x, pad_mask).masked_fill(pad_mask.unsqueeze(-1), 0)
         return self.pos_ffn(x).masked_fill(pad_mask.unsqueeze(-1), 0)
+
+    # ---- B200 path (bf16 mode): projections / conv-FFN / LayerNorm on the library's tcgen05 GEMM and row-LN
+    # kernels (flm_conv1d_bf16, flm_layernorm_bf16), attention through torch's fused SDPA (library kernel)
+    def _pack(self, device):
+        a, f = self.slf_attn, self.pos_ffn
+        key = (str(device), a.w_qs.weight._version, f.w_1.weight._version, a.w_qs.weight.data_ptr())
+        if self._packed is None or self._packed["key"] != key:
+            bf = lambda t: t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+            f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._packed = dict(
+                key=key,
+                wqkv=bf(torch.cat([a.w_qs.weight, a.w_ks.weight, a.w_vs.weight], 0)).unsqueeze(0),  # (1, 3D, D)
+                bqkv=f32(torch.cat([a.w_qs.bias, a.w_ks.bias, a.w_vs.bias], 0)),
+                wfc=bf(a.fc.weight).unsqueeze(0), bfc=f32(a.fc.bias),
+                ln1w=f32(a.layer_norm.weight), ln1b=f32(a.layer_norm.bias),
+                w1=bf(f.w_1.weight.permute(2, 0, 1)), b1=f32(f.w_1.bias),     # (k, d_hid, d_in) tap-major
+                w2=bf(f.w_2.weight.permute(2, 0, 1)), b2=f32(f.w_2.bias),
+                ln2w=f32(f.layer_norm.weight), ln2b=f32(f.layer_norm.bias),
+                k1=f.w_1.kernel_size[0], k2=f.w_2.kernel_size[0])
+        return self._packed
+
+    def forward_b200(self, ctx, x, pad_u8, attn_bias):
+        """x (B,S,D) bf16 contiguous, pad_u8 (B,S) uint8 1 = padding, attn_bias (B,1,1,S) bf16 additive key mask"""
+        from flamed_tts_b200.engines import conv1d_bf16, layernorm_bf16
+        w = self._pack(x.device)
+        B, S, D = x.shape
+        H = self.slf_attn.n_head
+        qkv = conv1d_bf16(ctx, x, w["wqkv"], w["bqkv"]).view(B, S, 3, H, D // H)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))                 # (B,H,S,dh) strided views
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_bias)
+        o = o.transpose(1, 2).reshape(B, S, D)
+        y = conv1d_bf16(ctx, o, w["wfc"], w["bfc"], epi=4, resid=x)                # fc(o) + x
+        x = layernorm_bf16(ctx, y, w["ln1w"], w["ln1b"], self.slf_attn.layer_norm.eps, zero_rows=pad_u8, out=y)
+        h = conv1d_bf16(ctx, x, w["w1"], w["b1"], epi=3, off0=-(w["k1"] // 2))      # relu(conv k)
+        y = conv1d_bf16(ctx, h, w["w2"], w["b2"], epi=4, off0=-(w["k2"] // 2), resid=x)
+        return layernorm_bf16(ctx, y, w["ln2w"], w["ln2b"], self.pos_ffn.layer_norm.eps, zero_rows=pad_u8, out=y)
 
 
 class _Stack(nn.Module):
@@ -78,8 +115,21 @@ class _Stack(nn.Module):
             return sinusoid_table(L, self.d_model).unsqueeze(0).to(device)
         return self.position_enc[:, :L]
 
+    b200 = False  # set by the owner (PriorGenerator) in bf16 mode: run the blocks on the library's kernels
+
     def _run(self, x, pad_mask):
         x = x + self._positions(x.shape[1], x.device).to(x.dtype)
+        if self.b200 and x.is_cuda and x.shape[-1] % 128 == 0:
+            from flamed_tts_b200.engines import Context
+            ctx = Context.get(x.device)
+            out_dtype = x.dtype
+            x = x.to(torch.bfloat16).contiguous()
+            pad_u8 = pad_mask.to(torch.uint8).contiguous()
+            bias = torch.zeros((x.shape[0], 1, 1, x.shape[1]), dtype=torch.bfloat16, device=x.device)
+            bias.masked_fill_(pad_mask[:, None, None, :], float("-inf"))
+            for blk in self.layer_stack:
+                x = blk.forward_b200(ctx, x, pad_u8, bias)
+            return x.to(out_dtype) if out_dtype != torch.bfloat16 else x
         for blk in self.layer_stack:
             x = blk(x, pad_mask)
         return x

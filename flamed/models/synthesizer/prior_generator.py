@@ -5,6 +5,8 @@ parameter names).  Only `pva` is on the B200 kernel path; the FFT stacks are PyT
  and run under bf16 autocast when the model precision is 'bf16'
 (the phoneme encoder always stays fp32: rounded durations must match the reference).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -58,6 +60,10 @@ class PriorGenerator(nn.Module):
     @torch.inference_mode()
     def decode_priors(self, x, tgt_lens, prompts, prompts_len, bf16=False):
         """length-regulated encoder output (B,L,192) -> (embs, logits, tgt_mask); prior_generator.py:162-181"""
+        fast = bf16 and x.is_cuda and os.environ.get("FLAMED_B200_FFT", "kernels") != "torch"
+        self.shared_decoder.b200 = fast
+        for d in self.prior_decoder:
+            d.b200 = fast
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16), \
                 torch.backends.cudnn.flags(enabled=True, allow_tf32=bf16):
             x = self.bridge(x)

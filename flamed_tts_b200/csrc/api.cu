@@ -1009,6 +1009,48 @@ extern "C" int flm_tapgemm_test_bf16(flm_ctx* ctx, int gen, const void* A, const
   FLM_API_END
 }
 
+// ===================================================================================== generic bf16 ops
+// Building blocks for callers next to the hot path (the prior generator's FFT stacks): the same
+// tcgen05 implicit-conv GEMM and row LayerNorm the denoiser uses, on caller-owned bf16 tensors.
+extern "C" int flm_conv1d_bf16(flm_ctx* ctx, const void* A, const void* W, const float* bias, int B, int T, int K, int N,
+                               int ntaps, int off0, int dil, int epi, void* out, const void* resid, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && A && W && out, "null argument");
+  FLM_REQUIRE(epi >= EPI_NONE && epi <= EPI_RESID, "epi must be 0..4");
+  FLM_REQUIRE(epi != EPI_RESID || resid != nullptr, "epi 4 needs resid");
+  set_device(ctx);
+  if ((int64_t)B * T == 0) return FLM_OK;
+  TapGemm p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.W = W; p.bias = bias; p.out = out; p.lda = K; p.ldc = N; p.B = B; p.T_in = T; p.T_out = T; p.K = K; p.N = N;
+  p.ntaps = ntaps; p.off0 = off0; p.dil = dil; p.stride = 1; p.epi = epi; p.out_bf16 = 1; p.resid_in = resid;
+  FLM_REQUIRE(tapgemm_tc_supported(p), "conv1d_bf16: need K % 64 == 0, N % 64 == 0 and 16-byte aligned operands");
+  const double M = (double)B * T;
+  char tag[96];
+  tag[0] = 0;
+  if (ctx->prof_on) snprintf(tag, sizeof(tag), "K%d N%d taps%d epi%d B%d T%d", K, N, ntaps, epi, B, T);
+  ProfScope ps(ctx, KC_GEMM_TC, S(stream), 2.0 * M * N * K * ntaps, M * K * 2 + (double)ntaps * N * K * 2 + M * N * 2, tag);
+  if (ctx->gemm_gen >= 2 && tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, S(stream));
+  else launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, S(stream));
+  FLM_API_END
+}
+
+// y = LayerNorm(x; w, b, eps) row-wise over C, rows with zero_rows[r] != 0 written as zeros; x, y bf16 (rows, C)
+extern "C" int flm_layernorm_bf16(flm_ctx* ctx, const void* x, const float* w, const float* b, float eps, int64_t rows,
+                                  int C, const uint8_t* zero_rows, void* y, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && x && y, "null argument");
+  set_device(ctx);
+  if (rows == 0) return FLM_OK;
+  LnMod ln;
+  memset(&ln, 0, sizeof(ln));
+  ln.x = x; ln.ldx = C; ln.x_bf16 = 1; ln.y = y; ln.ldy = C; ln.y_bf16 = 1; ln.w = w; ln.b = b; ln.scale_plus_one = 1.f;
+  ln.eps = eps; ln.rows = rows; ln.rows_per_batch = (int)std::min<int64_t>(rows, 1 << 30); ln.C = C; ln.zero_rows = zero_rows;
+  ProfScope ps(ctx, KC_LN_MOD, S(stream), (double)rows * C * 8, (double)rows * C * 4);
+  launch_ln_mod(ln, S(stream));
+  FLM_API_END
+}
+
 // ---- micro-benchmark hook: `reps` back-to-back launches of one tap-GEMM on pseudo-random operands,
 // timed with CUDA events on `stream`; *out_ms = average ms per launch.  epi 0..3, or 5 (gated residual).
 // Operands are pseudo-random (zeros would under-state the power draw and over-state the clocks).

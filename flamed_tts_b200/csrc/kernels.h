@@ -31,6 +31,7 @@ struct LnMod {
   float eps;
   int64_t rows; int rows_per_batch; int C;
   int relu_in;  // apply ReLU to x before the statistics (durgen: LN(ReLU(conv)))
+  const uint8_t* zero_rows;  // nullable (rows): non-zero -> the output row is all zeros (FFT blocks: masked_fill of padding)
 };
 void launch_ln_mod(const LnMod& p, cudaStream_t stream);
 

@@ -128,12 +128,13 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
         q = fmaf(v[i][j], v[i][j], q);
       }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)C) + p.eps);
+    const bool zero = p.zero_rows != nullptr && p.zero_rows[row] != 0;  // warp-uniform
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       float o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = fmaf(v[i][j] * rstd, A[i][j], Bv[i][j]);
+      for (int j = 0; j < 4; ++j) o[j] = zero ? 0.f : fmaf(v[i][j] * rstd, A[i][j], Bv[i][j]);
       if (p.y_bf16)
         st4<bf16>(static_cast<bf16*>(p.y) + row * p.ldy + c, o);
       else

@@ -277,3 +277,29 @@ def tapgemm(ctx, precision, A, W, bias, T_out, ntaps, off0, dil, stride, epi):
     check(ctx.lib.flm_tapgemm_test(ctx.handle, _mode(precision), _ptr(A), _ptr(W), _ptr(bias), B, T_in, T_out, K, N,
                                    ntaps, off0, dil, stride, epi, _ptr(out), ctx.stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ generic bf16 ops
+def conv1d_bf16(ctx, a, w, bias, epi=0, off0=0, dil=1, resid=None, out=None):
+    """a (B,T,K) bf16, w (ntaps,N,K) bf16 packed tap-major, bias (N) f32 or None -> (B,T,N) bf16 through the tcgen05
+    implicit-conv GEMM (flm_conv1d_bf16).  epi: 0 none, 1 gelu, 2 silu, 3 relu, 4 out = resid + v."""
+    B, T, K = a.shape
+    ntaps, N, _ = w.shape
+    if out is None:
+        out = torch.empty((B, T, N), device=a.device, dtype=torch.bfloat16)
+    check(ctx.lib.flm_conv1d_bf16(ctx.handle, _ptr(a), _ptr(w), _ptr(bias), B, T, K, N, ntaps, off0, dil, epi, _ptr(out),
+                                  _ptr(resid), ctx.stream()))
+    return out
+
+
+def layernorm_bf16(ctx, x, w, b, eps, zero_rows=None, out=None):
+    """row LayerNorm of x (..., C) bf16 with fp32 affine; rows flagged in zero_rows (uint8/bool, one per row) -> 0"""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    if zero_rows is not None and zero_rows.dtype != torch.uint8:
+        zero_rows = zero_rows.to(torch.uint8)
+    check(ctx.lib.flm_layernorm_bf16(ctx.handle, _ptr(x), _ptr(w), _ptr(b), float(eps), rows, C, _ptr(zero_rows), _ptr(out),
+                                     ctx.stream()))
+    return out

@@ -161,6 +161,18 @@ int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const float* W, con
                      int T_out, int K, int N, int ntaps, int off0, int dil, int stride, int epi, float* out,
                      flm_stream stream);
 
+/* ---------------------------------------------------------------- generic bf16 building blocks
+ * The denoiser's tcgen05 implicit-conv GEMM and row LayerNorm on caller-owned device bf16 tensors, for the callers
+ * either side of the hot path (the prior generator's FFT decoder stacks, Models.py:107-171 / SubLayers.py:8-93).
+ * flm_conv1d_bf16: out[b,t,n] = epi(sum_tap sum_k A[b,t+off0+tap*dil,k] W[tap][n][k] + bias[n]); A (B,T,K),
+ * W (ntaps,N,K), out/resid (B,T,N) bf16; bias (N) f32; K % 64 == 0, N % 64 == 0; epi 0 none, 1 gelu, 2 silu, 3 relu,
+ * 4 out = resid + v.  flm_layernorm_bf16: y = LN(x; w, b, eps) over the last dim (C % 128 == 0, C <= 1024), rows with
+ * zero_rows[r] != 0 (nullable) are written as zeros - the masked_fill(pad, 0) that follows every FFT sub-layer. */
+int flm_conv1d_bf16(flm_ctx* ctx, const void* A, const void* W, const float* bias, int B, int T, int K, int N, int ntaps,
+                    int off0, int dil, int epi, void* out, const void* resid, flm_stream stream);
+int flm_layernorm_bf16(flm_ctx* ctx, const void* x, const float* w, const float* b, float eps, int64_t rows, int C,
+                       const uint8_t* zero_rows, void* y, flm_stream stream);
+
 /* bf16-in / bf16-out form of the same problem on the tcgen05 kernels: gen 1 = single-CTA kernel, 2 = CTA-pair
  * (cta_group::2) kernel with the TMA epilogue.  A, W, out, resid, addend are device bf16; bias (N) and gate (B,N)
  * are f32.  epi 0..3 as above; 4: out = resid + v (codec skip connection, facodec.py:131-133);

@@ -110,6 +110,58 @@ def test_tapgemm_tcgen05_matches_fp32_kernel():
     assert r.returncode == 0 and "OK" in r.stdout
 
 
+def test_tapgemm_cta_pair_kernel_vs_torch_and_first_generation():
+    """tapgemm_tc2.cu (cta_group::2 + TMA slab epilogue): every epilogue (none/GELU/SiLU/ReLU, codec skip, adaLN-gated
+    residual with and without the ConvNeXt addend), flattened and per-sample tilings, ragged tails, odd tile counts,
+    dilated taps - against a torch fp32 restatement on the same bf16 operands (rel-L2 <= 4e-3 = bf16 output
+    rounding) and bit-for-bit against the single-CTA kernel.  Subprocess + timeout: a dead-lock must not hang."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tc2_check.py")], capture_output=True, text=True,
+                       timeout=240)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "ALL OK" in r.stdout
+    assert "gen1 vs gen2 max-abs 0.000e+00" in r.stdout
+
+
+_DW_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, %r)
+os.environ["FLAMED_B200_DWCONV"] = %r
+if %r: os.environ["FLAMED_B200_DWCONV_V1"] = "1"
+import torch, yaml
+from flamed_tts_b200 import synthetic as W
+from flamed_tts_b200.engines import Context, DenoiserEngine
+from oracle import flamed_oracle as O
+ROOT = %r
+prior = yaml.safe_load(open(os.path.join(ROOT, "configs", "prior.yaml")))
+prob = yaml.safe_load(open(os.path.join(ROOT, "configs", "prob.yaml")))
+sd = W.make_flamed_state_dict(prior, prob, 0)
+psd = {k[len("prob_generator."):]: v for k, v in sd.items() if k.startswith("prob_generator.")}
+ctx = Context.get("cuda:0")
+den = DenoiserEngine(ctx, psd, prob, "bf16")
+g = torch.Generator().manual_seed(5)
+B, L = 3, 333   # ragged: 333 = 2*128 + 77 frames, 10 full 32-frame chunks + 13
+x = torch.randn(B, L, 256, generator=g)
+spk = torch.randn(B, 256, generator=g)
+v = den.forward(x.cuda(), 0.37, spk.cuda()).float().cpu()
+with torch.inference_mode():
+    ref = O.denoiser_forward(psd, "denoiser", x, torch.full((1, 1), 0.37), spk)
+err = float((v - ref).norm() / ref.norm())
+print("velocity rel-L2 %%.3e" %% err)
+assert err < 1e-2, err
+print("OK")
+"""
+
+
+@pytest.mark.parametrize("variant", ["fma-persistent", "fma-v1", "tensor"])
+def test_depthwise_conv_variants(variant):
+    """the three depthwise-conv kernels of the bf16 mode (persistent TMA-pipelined FMA = default, first FMA kernel,
+    tensor-core experiment) give a velocity within the bf16 tolerance (<= 1e-2) of the oracle on a ragged batch"""
+    mode, v1 = {"fma-persistent": ("fma", False), "fma-v1": ("fma", True), "tensor": ("tensor", False)}[variant]
+    r = subprocess.run([sys.executable, "-c", _DW_SCRIPT % (ROOT, mode, v1, ROOT)], capture_output=True, text=True, timeout=240)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "OK" in r.stdout
+
+
 # ------------------------------------------------------------------------------------------------ modules
 @pytest.fixture(scope="module")
 def engines(ctx, cfg, flamed_sd, codec_dec_sd, codec_enc_sd):
