@@ -350,12 +350,15 @@ def main():
         k = kernels[top]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top)
+        traffic_detail = None
+        if os.path.exists(tpath):  # DRAM bytes per launch of the top kernel from the committed ncu --set full capture
+            traffic_detail = json.load(open(tpath)).get(top)
+            traffic = traffic_detail.get("dram_bytes_read_plus_write_per_launch") if isinstance(traffic_detail, dict) else traffic_detail
         roof = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"],
                 "peak": pk["bf16_tflops_sustained"] if k["bound"] == "tensor" else pk["hbm_gbs"], "unit": k["unit"],
                 "frac": k["frac"], "traffic": traffic, "peak_source": pk["source"] + (" (sustained bf16)" if k["bound"] == "tensor" else " (copy)"),
-                "avg_launch_ms": round(prof[top]["ms"] / prof[top]["launches"], 4), "profiled_step_ms": round(prof_wall, 1)}
+                "avg_launch_ms": round(prof[top]["ms"] / prof[top]["launches"], 4), "profiled_step_ms": round(prof_wall, 1),
+                "traffic_detail": traffic_detail}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
