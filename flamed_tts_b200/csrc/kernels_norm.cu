@@ -144,6 +144,139 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
   }
 }
 
+// bf16 -> bf16 form with packed fp32x2 arithmetic (ncu on the generic kernel: 56 % issue-slot utilisation at
+// 5 TB/s, i.e. instruction-bound before HBM-bound): lane = NCH chunks of 8 contiguous channels (one LDS.128 /
+// ST.128 each), statistics, normalisation and the folded affine as FADD2 / FFMA2 on channel pairs - half the
+// floating-point instructions per row.  Same ring / row ownership as ln_mod_kernel.
+template <int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_bf16_kernel(LnMod p, int64_t rows_per_warp) {
+  constexpr int C = NCH * 256;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bf16* ring = reinterpret_cast<bf16*>(ln_smem) + (size_t)warp * LN_DEPTH * C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)LN_WARPS * LN_DEPTH * C * sizeof(bf16)) + warp * LN_DEPTH;
+  const int64_t gw = (int64_t)blockIdx.x * LN_WARPS + warp;
+  const int64_t r_begin = gw * rows_per_warp;
+  const int64_t r_end = min(p.rows, r_begin + rows_per_warp);
+  if (r_begin >= r_end) return;
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < LN_DEPTH; ++d)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(&bars[d])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int64_t r, int slot) {  // lane 0 only
+    const uint32_t bar = ln_smem_u32(&bars[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * 2)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ln_smem_u32(ring + (size_t)slot * C)),
+                 "l"(static_cast<const bf16*>(p.x) + r * p.ldx), "r"((uint32_t)(C * 2)), "r"(bar)
+                 : "memory");
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < LN_DEPTH; ++d)
+      if (r_begin + d < r_end) issue(r_begin + d, d);
+  }
+  f32x2 A2[NCH][4], B2[NCH][4];
+  int cur_b = -1;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t row = r_begin; row < r_end; ++row) {
+    {
+      const uint32_t bar = ln_smem_u32(&bars[slot]);
+      uint32_t done;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(phase)
+            : "memory");
+      } while (!done);
+    }
+    f32x2 v[NCH][4];
+    const bf16* xs = ring + (size_t)slot * C;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const uint4 q = *reinterpret_cast<const uint4*>(xs + (i * 32 + lane) * 8);
+      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = pack2(__uint_as_float(u[j] << 16), __uint_as_float(u[j] & 0xffff0000u));
+    }
+    __syncwarp();
+    if (lane == 0 && row + LN_DEPTH < r_end) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
+      issue(row + LN_DEPTH, slot);
+    }
+    const int bi = (int)(row / p.rows_per_batch);
+    if (bi != cur_b) {  // fold affine + modulation for this sample (warp-uniform branch)
+      cur_b = bi;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = (i * 32 + lane) * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float w[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, a[4], bb[4];
+          if (p.w) { ld4<float>(p.w + c + 4 * h, w); ld4<float>(p.b + c + 4 * h, b); }
+          if (p.scale) {
+            float sc[4], sh[4];
+            ld4<float>(p.scale + (int64_t)bi * p.mod_bstride + c + 4 * h, sc);
+            ld4<float>(p.shift + (int64_t)bi * p.mod_bstride + c + 4 * h, sh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float m = p.scale_plus_one + sc[j];
+              a[j] = w[j] * m;
+              bb[j] = fmaf(b[j], m, sh[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = w[j]; bb[j] = b[j]; }
+          }
+          A2[i][2 * h] = pack2(a[0], a[1]); A2[i][2 * h + 1] = pack2(a[2], a[3]);
+          B2[i][2 * h] = pack2(bb[0], bb[1]); B2[i][2 * h + 1] = pack2(bb[2], bb[3]);
+        }
+      }
+    }
+    f32x2 s2 = 0ull;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s2 = add2(s2, v[i][j]);
+    float s_lo, s_hi;
+    unpack2(s2, s_lo, s_hi);
+    const float mean = warp_sum(s_lo + s_hi) * (1.0f / (float)C);
+    const f32x2 negm = pack2(-mean, -mean);
+    f32x2 q2 = 0ull;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][j] = add2(v[i][j], negm);
+        q2 = fma2(v[i][j], v[i][j], q2);
+      }
+    float q_lo, q_hi;
+    unpack2(q2, q_lo, q_hi);
+    const float rstd = rsqrtf(warp_sum(q_lo + q_hi) * (1.0f / (float)C) + p.eps);
+    const f32x2 r2 = pack2(rstd, rstd);
+    const bool zero = p.zero_rows != nullptr && p.zero_rows[row] != 0;  // warp-uniform
+    bf16* yrow = static_cast<bf16*>(p.y) + row * p.ldy;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        unpack2(fma2(mul2(v[i][j], r2), A2[i][j], B2[i][j]), lo, hi);
+        __nv_bfloat162 t = __floats2bfloat162_rn(zero ? 0.f : lo, zero ? 0.f : hi);
+        o[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *reinterpret_cast<uint4*>(yrow + (i * 32 + lane) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (++slot == LN_DEPTH) { slot = 0; phase ^= 1; }
+  }
+}
+
 template <int NV, typename TI>
 constexpr int ln_smem_bytes() { return LN_WARPS * LN_DEPTH * NV * 128 * (int)sizeof(TI) + LN_WARPS * LN_DEPTH * 8; }
 template <int NV>
@@ -152,6 +285,9 @@ void ln_set_attr() {
                                 ln_smem_bytes<NV, float>()));
   FLM_CUDA(cudaFuncSetAttribute(ln_mod_kernel<NV, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ln_smem_bytes<NV, bf16>()));
+  if (NV % 2 == 0)
+    FLM_CUDA(cudaFuncSetAttribute(ln_mod_bf16_kernel<(NV >= 2 ? NV / 2 : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ln_smem_bytes<NV, bf16>()));
 }
 
 template <int NV>
@@ -160,7 +296,10 @@ void ln_launch(const LnMod& p, int sms, cudaStream_t stream) {
   if (blocks > sms) blocks = sms;
   const int64_t total_warps = blocks * LN_WARPS;
   const int64_t rpw = (p.rows + total_warps - 1) / total_warps;
-  if (p.x_bf16)
+  if (p.x_bf16 && p.y_bf16 && !p.relu_in && NV % 2 == 0 && p.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+      !getenv("FLAMED_B200_LN_V1"))
+    ln_mod_bf16_kernel<(NV >= 2 ? NV / 2 : 1)><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, bf16>(), stream>>>(p, rpw);
+  else if (p.x_bf16)
     ln_mod_kernel<NV, bf16><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, bf16>(), stream>>>(p, rpw);
   else
     ln_mod_kernel<NV, float><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, float>(), stream>>>(p, rpw);
@@ -447,14 +586,26 @@ __global__ void __launch_bounds__(128) dwconv_tma_kernel(const __grid_constant__
     const int nvalid = min(DW_TT, p.L - t0);
     bf16* yb = static_cast<bf16*>(p.y) + ((int64_t)b * p.L + t0) * p.C + c;
     f32x2 s2 = 0ull;
+    if (nvalid == DW_TT) {  // full chunk: no predicates, running pointer
 #pragma unroll
-    for (int j = 0; j < DW_TT; ++j) {
-      acc[j] = add2(acc[j], bias2);
-      if (j < nvalid) {
+      for (int j = 0; j < DW_TT; ++j) {
+        acc[j] = add2(acc[j], bias2);
         float a0, a1;
         unpack2(acc[j], a0, a1);
-        st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
+        st2<bf16>(yb, a0, a1);
+        yb += p.C;
         s2 = add2(s2, acc[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DW_TT; ++j) {
+        acc[j] = add2(acc[j], bias2);
+        if (j < nvalid) {
+          float a0, a1;
+          unpack2(acc[j], a0, a1);
+          st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
+          s2 = add2(s2, acc[j]);
+        }
       }
     }
     float s0, s1;
