@@ -507,8 +507,7 @@ __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
 // unit = the conv's zero padding), issued DWP_STAGES-1 tiles ahead by thread 0, so ~2-3 tiles (60-90 KB) per
 // block are in flight while the 31-tap FFMA2 window runs; the tap weights stay in registers for the whole
 // kernel because the grid is a multiple of the number of channel blocks.
-constexpr int DWP_STAGES = 3;
-template <int KW>
+template <int KW, int DWP_STAGES>
 __global__ void __launch_bounds__(128) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, DwConv p, int nchunk,
                                                          int ncblk, int ntiles) {
   constexpr int PAD = KW / 2;
@@ -586,43 +585,40 @@ __global__ void __launch_bounds__(128) dwconv_tma_kernel(const __grid_constant__
     const int nvalid = min(DW_TT, p.L - t0);
     bf16* yb = static_cast<bf16*>(p.y) + ((int64_t)b * p.L + t0) * p.C + c;
     f32x2 s2 = 0ull;
+    // statistics about the pivot bias[c] (acc holds y - bias): S = sum acc, Q = sum acc^2 -> mean = bias + S/n,
+    // M2 = Q - S^2/n; the bias is added on the way out
+    f32x2 q2 = 0ull;
     if (nvalid == DW_TT) {  // full chunk: no predicates, running pointer
 #pragma unroll
       for (int j = 0; j < DW_TT; ++j) {
-        acc[j] = add2(acc[j], bias2);
+        s2 = add2(s2, acc[j]);
+        q2 = fma2(acc[j], acc[j], q2);
         float a0, a1;
-        unpack2(acc[j], a0, a1);
+        unpack2(add2(acc[j], bias2), a0, a1);
         st2<bf16>(yb, a0, a1);
         yb += p.C;
-        s2 = add2(s2, acc[j]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < DW_TT; ++j) {
-        acc[j] = add2(acc[j], bias2);
         if (j < nvalid) {
-          float a0, a1;
-          unpack2(acc[j], a0, a1);
-          st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
           s2 = add2(s2, acc[j]);
+          q2 = fma2(acc[j], acc[j], q2);
+          float a0, a1;
+          unpack2(add2(acc[j], bias2), a0, a1);
+          st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
         }
       }
     }
-    float s0, s1;
+    float s0, s1, q0, q1, b0, b1;
     unpack2(s2, s0, s1);
-    const float inv = 1.0f / (float)nvalid;
-    const float m0 = s0 * inv, m1 = s1 * inv;
-    const f32x2 negm = pack2(-m0, -m1);
-    f32x2 q2 = 0ull;
-#pragma unroll
-    for (int j = 0; j < DW_TT; ++j) {
-      if (j < nvalid) {
-        const f32x2 d = add2(acc[j], negm);
-        q2 = fma2(d, d, q2);
-      }
-    }
-    float q0, q1;
     unpack2(q2, q0, q1);
+    unpack2(bias2, b0, b1);
+    const float inv = 1.0f / (float)nvalid;
+    const float d0 = s0 * inv, d1 = s1 * inv;
+    const float m0 = b0 + d0, m1 = b1 + d1;
+    q0 = fmaxf(q0 - s0 * d0, 0.f);
+    q1 = fmaxf(q1 - s1 * d1, 0.f);
     float* part = p.part + (((int64_t)b * nchunk + chunk) * p.C + c) * 2;
     *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
     if (++slot == DWP_STAGES) { slot = 0; phase ^= 1; }
@@ -778,10 +774,18 @@ void launch_dwconv(const DwConv& p, cudaStream_t stream) {
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    int per_cblk = (2 * sms) / ncblk;  // two resident blocks per SM
+    // 3-deep ring with two resident blocks per SM by default; FLAMED_B200_DWCONV_RING=2 selects a 2-deep ring with
+    // three blocks per SM (12 warps) - measured equal (5.0 vs 5.1 ms per 40 launches at 79k frames): the kernel is
+    // FMA-pipe bound, not latency bound
+    static const bool ring3 = [] { const char* e = getenv("FLAMED_B200_DWCONV_RING"); return !(e && atoi(e) == 2); }();
+    const int ctas_per_sm = ring3 ? 2 : 3;
+    int per_cblk = (ctas_per_sm * sms) / ncblk;
     if (per_cblk > ntiles) per_cblk = ntiles;
     if (per_cblk < 1) per_cblk = 1;
-    dwconv_tma_kernel<31><<<per_cblk * ncblk, 128, DWP_STAGES * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
+    if (ring3)
+      dwconv_tma_kernel<31, 3><<<per_cblk * ncblk, 128, 3 * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
+    else
+      dwconv_tma_kernel<31, 2><<<per_cblk * ncblk, 128, 2 * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
     FLM_LAUNCH_CHECK();
     launch_dw_merge(p, stream);
     return;
@@ -996,8 +1000,8 @@ void kernels_norm_init() {
   constexpr int ROWS = DW_TT + 31 - 1;
   FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<float, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 4));
   FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<bf16, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 2));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                DWP_STAGES * ROWS * 256 * 2 + 64));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * ROWS * 256 * 2 + 64));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ROWS * 256 * 2 + 64));
 }
 
 void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, float* part, cudaStream_t stream) {
