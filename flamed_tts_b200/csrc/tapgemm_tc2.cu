@@ -77,8 +77,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on a barrier of the leader CTA.  Default (.release.cta) semantics on purpose: what the barrier orders is
+// TMEM traffic (tcgen05.fence::before_thread_sync precedes it); a .release.cluster here costs an ERRBAR per arrive
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -93,20 +95,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// wait that also orders against arrivals performed by the peer CTA (cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
+// Waits on barriers that the peer CTA / the multicast tcgen05.commit arrive on use the same CTA-scope wait: the
+// data they guard moves through the async proxy (TMA -> smem, tcgen05 -> TMEM), never through generic-proxy
+// global/shared accesses of the peer.  An .acquire.cluster wait makes ptxas emit CCTL.IVALL after every wait: the L1
+// invalidation evicted the bias / gate vectors every tile (ncu: 30 % of the epilogue's stall samples, profiles/r01k).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -420,51 +413,73 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
 #pragma unroll 1
       for (int s = 0; s < SLABS; ++s) {
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)(s * SLAB_COLS + half * 32), v);
         const int n = nt * BLOCK_N + s * SLAB_COLS + half * 32;
+        // per-column operands first: their (L1) latency hides behind the TMEM load and the slab barrier
+        float4 bq[8], gq[8];
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          for (int j = 0; j < 8; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+        }
+        if (EPI == EPI_GATE_RESID) {
+          const float4* gp = reinterpret_cast<const float4*>(p.gate + (int64_t)bidx * p.gate_bstride + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gq[j] = __ldg(gp + j);
+        }
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)(s * SLAB_COLS + half * 32), v);
+        // packed fp32x2 from here on: a2[i] = columns (2i, 2i+1)
+        f32x2 a2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a2[i] = pack2(v[2 * i], v[2 * i + 1]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a2[2 * j] = add2(a2[2 * j], pack2(bq[j].x, bq[j].y));
+            a2[2 * j + 1] = add2(a2[2 * j + 1], pack2(bq[j].z, bq[j].w));
           }
         }
         uint8_t* rrow_ptr = smem_r + buf * SLAB_BYTES + rrow * 128;
         if (kResid) {
           mbar_wait(&r_full[buf], bphase);
-          if (EPI == EPI_GATE_RESID) {
-            if (has_addend) {
-              const uint8_t* drow_ptr = smem_d + buf * SLAB_BYTES + rrow * 128;
+          if (EPI == EPI_GATE_RESID && has_addend) {
+            const uint8_t* drow_ptr = smem_d + buf * SLAB_BYTES + rrow * 128;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint4 q = *reinterpret_cast<const uint4*>(drow_ptr + (((half * 4 + c) ^ (rrow & 7)) << 4));
-                float f[8];
-                unpack_bf16x8(q, f);
+            for (int c = 0; c < 4; ++c) {
+              const uint4 q = *reinterpret_cast<const uint4*>(drow_ptr + (((half * 4 + c) ^ (rrow & 7)) << 4));
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[c * 8 + j] += f[j];
-              }
-            }
-            const float* gp = p.gate + (int64_t)bidx * p.gate_bstride + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 g = __ldg(reinterpret_cast<const float4*>(gp + j));
-              v[j] = __fmul_rn(g.x, v[j]); v[j + 1] = __fmul_rn(g.y, v[j + 1]);
-              v[j + 2] = __fmul_rn(g.z, v[j + 2]); v[j + 3] = __fmul_rn(g.w, v[j + 3]);
+              for (int j = 0; j < 4; ++j)
+                a2[c * 4 + j] = add2(a2[c * 4 + j], pack2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u)));
             }
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4* slot = reinterpret_cast<uint4*>(rrow_ptr + (((half * 4 + c) ^ (rrow & 7)) << 4));
-            float f[8];
-            unpack_bf16x8(*slot, f);
+            const uint4 q = *slot;
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __fadd_rn(f[j], v[c * 8 + j]);
-            *slot = pack_bf16x8(f);
+            for (int j = 0; j < 4; ++j) {
+              const f32x2 h2 = pack2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
+              f32x2 r2;
+              if (EPI == EPI_GATE_RESID) {  // h + g * (acc + bias + u): one fused multiply-add per element (bf16 result)
+                const float4 g = gq[c * 2 + (j >> 1)];
+                r2 = fma2((j & 1) ? pack2(g.z, g.w) : pack2(g.x, g.y), a2[c * 4 + j], h2);
+              } else {
+                r2 = add2(h2, a2[c * 4 + j]);
+              }
+              float lo, hi;
+              unpack2(r2, lo, hi);
+              __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+              o[j] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *slot = make_uint4(o[0], o[1], o[2], o[3]);
           }
         } else {
-          mbar_wait(&r_free[buf], bphase ^ 1);  // the previous store out of this buffer has read it
+#pragma unroll
+          for (int i = 0; i < 16; ++i) unpack2(a2[i], v[2 * i], v[2 * i + 1]);
           act_fast32<EPI>(v);
+          mbar_wait(&r_free[buf], bphase ^ 1);  // the previous store out of this buffer has read it
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(rrow_ptr + (((half * 4 + c) ^ (rrow & 7)) << 4)) = pack_bf16x8(&v[c * 8]);
