@@ -141,6 +141,21 @@ def run_step(model, dec, batches, args, device, from_host, host_out=None):
     """one pass over all batches.  from_host: inputs are copied from pinned host memory inside the step and
     the waveforms are read back into pinned host buffers (the e2e leg)."""
     tgt_lens, wavs = [], []
+    if getattr(args, "pipelined", True):
+        # the metadata entry point: Flamed.sample_batches overlaps the front stage (duration ODEs + the path's one host
+        # sync) of bucket i+1 with the denoiser / codec kernels of bucket i
+        def on_result(bi, out):
+            tgt_lens.append((~out["tgt_mask"]).sum(1))
+            if from_host:
+                w = out["wav"]
+                if host_out[bi] is None or host_out[bi].shape != w.shape:
+                    host_out[bi] = torch.empty(w.shape, dtype=w.dtype).pin_memory()
+                host_out[bi].copy_(w, non_blocking=True)
+            wavs.append(out["wav"])
+        model.sample_batches([b if from_host else b["dev"] for b in batches], codec_decoder=dec,
+                             temp_durgen=args.temp_durgen, temp_denoiser=args.temp_denoiser,
+                             nsteps_durgen=args.nsteps_durgen, nsteps_denoiser=args.nsteps_denoiser, on_result=on_result)
+        return tgt_lens, wavs
     for bi, b in enumerate(batches):
         src = b if from_host else b["dev"]
         out = model.sample_batch(src["phonemes"].to(device, non_blocking=True), src["src_lens"].to(device, non_blocking=True),
@@ -248,6 +263,8 @@ def main():
     ap.add_argument("--ref-utts", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--sequential", dest="pipelined", action="store_false",
+                    help="loop over Flamed.sample_batch instead of the pipelined Flamed.sample_batches")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))

@@ -116,6 +116,61 @@ class Flamed(nn.Module):
             out["wav"] = codec_decoder.inference(latents, timbres)
         return out
 
+    @torch.inference_mode()
+    def sample_batches(self, batches, codec_decoder=None, temp_durgen=0.3, temp_denoiser=0.3, nsteps_durgen=64,
+                       nsteps_denoiser=64, on_result=None):
+        """Pipelined form of `sample_batch` for a list of length-bucketed batches (the synthesize_via_metadata
+        workload): the front stage of batch i+1 (phoneme encoder, duration ODEs, length regulator - small kernels
+        and the path's only host synchronisation) runs on a side stream while the denoiser / codec kernels of
+        batch i execute, so the device never drains between buckets.  `batches`: iterable of dicts with
+        phonemes (B,P), src_lens (B,), prompts (B,6,Lp), timbres (B,256) (host or device tensors).  Random draws happen in
+        the same order as a loop of `sample_batch` calls.  Returns the list of `sample_batch` result dicts
+        (or calls on_result(i, out) and returns None)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("Flamed.sample_batches: the hot path runs on a B200 (no CPU/PyTorch fallback)")
+        batches = list(batches)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side_stream", None) is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(dev)
+        side = self._side_stream
+
+        side.wait_stream(main)  # inputs the caller prepared on its stream; later fronts must NOT wait for `main`
+
+        def front(b):
+            with torch.cuda.stream(side):
+                t = {k: b[k].to(dev, non_blocking=True) for k in ("phonemes", "src_lens", "prompts", "timbres")}
+                x, tgt_lens = self.prior_generator.front(t["phonemes"], t["src_lens"], t["phonemes"].size(-1),
+                                                         nfe=nsteps_durgen, temperature=temp_durgen)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            for v in list(t.values()) + [x, tgt_lens]:
+                v.record_stream(main)
+            return t, x, tgt_lens, ev
+
+        outs = []
+        pending = front(batches[0]) if batches else None
+        for i in range(len(batches)):
+            t0 = time.time()
+            t, x, tgt_lens, ev = pending
+            main.wait_event(ev)
+            pg = self.prior_generator
+            prior_embs, prior_logits, tgt_mask = pg.decode_priors(
+                x, tgt_lens, t["prompts"], t["prompts"].size(-1), bf16=pg.pva.precision == "bf16" and x.is_cuda)
+            latents = self.prob_generator.sample(cond=prior_embs, spk=t["timbres"], nfe=nsteps_denoiser,
+                                                 temperature=temp_denoiser, mask=~tgt_mask.unsqueeze(-1))
+            out = {"prior_embs": prior_embs, "prior_logits": prior_logits, "tgt_mask": tgt_mask, "latents": latents,
+                   "time": time.time() - t0}
+            if codec_decoder is not None:
+                out["wav"] = codec_decoder.inference(latents, t["timbres"])
+            # everything of batch i is enqueued: the front stage of batch i+1 now overlaps its execution
+            pending = front(batches[i + 1]) if i + 1 < len(batches) else None
+            if on_result is not None:
+                on_result(i, out)
+            else:
+                outs.append(out)
+        return None if on_result is not None else outs
+
     # ------------------------------------------------------------------ pre-processing
     def _preprocess_acoustic_prompt(self, acoustic_prompt, sr=16000):
         if isinstance(acoustic_prompt, str):

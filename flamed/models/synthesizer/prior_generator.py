@@ -58,6 +58,15 @@ class PriorGenerator(nn.Module):
         return self.decode_priors(x, tgt_lens, prompts, prompts_len, bf16=self.pva.precision == "bf16" and x.is_cuda)
 
     @torch.inference_mode()
+    def front(self, texts, src_lens, max_src_len, nfe=4, temperature=1.0):
+        """first half of `sample`: phoneme encoder -> duration / silence ODEs -> length regulator.
+        Returns (x (B,L,192), tgt_lens (B,)); ends with the path's one host synchronisation (L is data dependent)."""
+        src_mask = get_mask_from_lengths(src_lens, max_src_len)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            enc = self.encoder(texts, src_mask)
+        return self.pva.sample(enc, src_lens, src_mask, nfe=nfe, temperature=temperature)
+
+    @torch.inference_mode()
     def decode_priors(self, x, tgt_lens, prompts, prompts_len, bf16=False):
         """length-regulated encoder output (B,L,192) -> (embs, logits, tgt_mask); prior_generator.py:162-181"""
         fast = bf16 and x.is_cuda and os.environ.get("FLAMED_B200_FFT", "kernels") != "torch"

@@ -135,6 +135,7 @@ def run_metadata(model, enc, dec, a):
         pending.sort(key=lambda e: -len(e[2]))
     cache, rtfs = {}, []
     pad_code = model.prior_generator.config["codec"]["vocab_size"]
+    groups, tensors = [], []
     for i in range(0, len(pending), a.batch_size):
         batch = pending[i:i + a.batch_size]
         seqs = [model._preprocess_english(t)[0].squeeze(0).cpu() for _, _, t in batch]
@@ -145,14 +146,20 @@ def run_metadata(model, enc, dec, a):
         prompts = torch.full((len(batch), feats[0][0].shape[0], lp), pad_code, dtype=feats[0][0].dtype)
         for j, (c, _) in enumerate(feats):
             prompts[j, :, : c.shape[-1]] = c
-        out = model.sample_batch(phon, lens, prompts, torch.stack([t for _, t in feats]), codec_decoder=dec,
-                                 temp_durgen=a.temp_durgen, temp_denoiser=a.temp_denoiser,
-                                 nsteps_durgen=a.nsteps_durgen, nsteps_denoiser=a.nsteps_denoiser)
-        per_item = out["time"] / len(batch)
-        for (out_path, _, _), w in zip(batch, out["wav"]):
+        groups.append(batch)
+        tensors.append(dict(phonemes=phon, src_lens=lens, prompts=prompts, timbres=torch.stack([t for _, t in feats])))
+
+    def on_result(i, out):  # bucket i is enqueued (bucket i+1's front stage already overlaps it): write it out
+        per_item = out["time"] / len(groups[i])
+        for (out_path, _, _), w in zip(groups[i], out["wav"]):
             wav = w[0].detach().cpu().numpy()  # padded batch length, as the reference writes it
             write_wav(out_path, wav)
             rtfs.append(per_item / (len(wav) / SR))
+
+    # Flamed.sample_batches = a loop of sample_batch calls (reference synthesize.py:270-299) with the front stage of
+    # the next bucket overlapped with the denoiser / codec kernels of the current one
+    model.sample_batches(tensors, codec_decoder=dec, temp_durgen=a.temp_durgen, temp_denoiser=a.temp_denoiser,
+                         nsteps_durgen=a.nsteps_durgen, nsteps_denoiser=a.nsteps_denoiser, on_result=on_result)
     return sum(rtfs) / len(rtfs) if rtfs else None
 
 

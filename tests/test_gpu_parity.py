@@ -432,6 +432,39 @@ def test_sample_batch_bf16_tolerance(dropin, gold):
     dec.set_precision("fp32")
 
 
+def test_sample_batches_pipelined_equals_sequential(dropin):
+    """Flamed.sample_batches (front stage of bucket i+1 on a side stream) returns exactly what a loop of
+    sample_batch calls returns: same draws (device generator, same order), same kernels, bit-identical tensors."""
+    model, enc, dec = dropin
+    model.set_precision("bf16").set_noise_device("cuda")
+    dec.set_precision("bf16")
+    g = torch.Generator().manual_seed(11)
+    batches = []
+    for B, P in ((3, 17), (2, 40), (4, 9)):
+        lens = torch.randint(max(2, P - 6), P + 1, (B,), generator=g)
+        lens[0] = P
+        ph = torch.randint(1, 70, (B, P), generator=g)
+        for i in range(B):
+            ph[i, lens[i]:] = 0
+        batches.append(dict(phonemes=ph, src_lens=lens, prompts=torch.randint(0, 1024, (B, 6, 30), generator=g),
+                            timbres=torch.randn(B, 256, generator=g)))
+    kw = dict(codec_decoder=dec, temp_durgen=0.3, temp_denoiser=0.3, nsteps_durgen=4, nsteps_denoiser=4)
+    try:
+        torch.manual_seed(3)
+        seq = [model.sample_batch(b["phonemes"], b["src_lens"], b["prompts"], b["timbres"], **kw) for b in batches]
+        torch.cuda.synchronize()
+        torch.manual_seed(3)
+        pipe = model.sample_batches(batches, **kw)
+        torch.cuda.synchronize()
+        assert len(pipe) == len(seq)
+        for a, b in zip(seq, pipe):
+            assert torch.equal(a["tgt_mask"], b["tgt_mask"])
+            assert torch.equal(a["latents"], b["latents"]) and torch.equal(a["wav"], b["wav"])
+    finally:
+        model.set_precision("fp32").set_noise_device("cpu")
+        dec.set_precision("fp32")
+
+
 def test_sample_single_utterance_with_raw_prompt(dropin):
     """Flamed.sample(phonemes=..., prompt_raw=...) end to end incl. the prompt encoder; shapes + finiteness,
     and idempotence for a fixed seed"""
