@@ -13,70 +13,86 @@ namespace flm {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+// 128 x 64 block tile, 8 x 4 outputs per thread (two 4-row groups 64 rows apart), BK = 16; the next k-block's global
+// loads are issued into registers before the current one is consumed (one __syncthreads pair per k-block, the
+// loads' latency overlapped with 512 FMAs per thread).  Every output still accumulates in ascending (tap, k)
+// order with one fmaf per term, so results are bit-identical to a plain dot-product loop.
+constexpr int BM = 128, BN = 64, BK = 16, TM = 8, TN = 4;
 
 __global__ void __launch_bounds__(256) tapgemm_simt_kernel(TapGemm p) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
   const float* __restrict__ A = static_cast<const float*>(p.A);
   const float* __restrict__ W = static_cast<const float*>(p.W);
   const int tid = threadIdx.x;
   const int64_t M = (int64_t)p.B * p.T_out;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
-  // loader mapping: row = tid / 4 (0..63), k-chunk = (tid % 4) * 4
+  // loader mapping: k-chunk = (tid % 4) * 4; A rows tid/4 and tid/4 + 64, W row tid/4
   const int lrow = tid >> 2, lk = (tid & 3) * 4;
-  const int64_t lm = m0 + lrow;
-  const bool lm_ok = lm < M;
-  const int lb = lm_ok ? (int)(lm / p.T_out) : 0;
-  const int lt = lm_ok ? (int)(lm % p.T_out) : 0;
+  int lb[2], lt[2];
+  bool lm_ok[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t lm = m0 + lrow + 64 * h;
+    lm_ok[h] = lm < M;
+    lb[h] = lm_ok[h] ? (int)(lm / p.T_out) : 0;
+    lt[h] = lm_ok[h] ? (int)(lm % p.T_out) : 0;
+  }
   const int ln = n0 + lrow;
   const bool ln_ok = ln < p.N;
-  // compute mapping
-  const int tr = (tid >> 4) * TM, tc = (tid & 15) * TN;
+  // compute mapping: rows tr..tr+3 and tr+64..tr+67, columns tc..tc+3
+  const int tr = (tid >> 4) * 4, tc = (tid & 15) * TN;
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int tap = 0; tap < p.ntaps; ++tap) {
-    const int tin = lt * p.stride + p.off0 + tap * p.dil;
-    const bool a_ok = lm_ok && tin >= 0 && tin < p.T_in;
-    const float* arow = A + ((int64_t)lb * p.T_in + (a_ok ? tin : 0)) * p.lda;
-    const float* wrow = W + ((int64_t)tap * p.N + (ln_ok ? ln : 0)) * p.K;
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
-      float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
-      const int k = k0 + lk;
-      if (k < p.K) {  // K % 4 == 0 is required, so a chunk is all-in or all-out
-        if (a_ok) ld4<float>(arow + k, av);
-        if (ln_ok) ld4<float>(wrow + k, wv);
+  const int kblocks = (p.K + BK - 1) / BK;
+  const int total = p.ntaps * kblocks;
+  float av[2][4], wv[4];
+  auto fetch = [&](int it) {  // global -> registers for iteration `it` = (tap, k-block)
+    const int tap = it / kblocks, k = (it % kblocks) * BK + lk;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { av[0][j] = 0.f; av[1][j] = 0.f; wv[j] = 0.f; }
+    if (k < p.K) {  // K % 4 == 0 is required, so a chunk is all-in or all-out
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int tin = lt[h] * p.stride + p.off0 + tap * p.dil;
+        if (lm_ok[h] && tin >= 0 && tin < p.T_in) ld4<float>(A + ((int64_t)lb[h] * p.T_in + tin) * p.lda + k, av[h]);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        As[lk + j][lrow] = av[j];
-        Bs[lk + j][lrow] = wv[j];
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < BK; ++kk) {
-        float a[TM], b[TN];
-#pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] = As[kk][tr + i];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tc + j];
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
+      if (ln_ok) ld4<float>(W + ((int64_t)tap * p.N + ln) * p.K + k, wv);
     }
+  };
+  fetch(0);
+  for (int it = 0; it < total; ++it) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      As[lk + j][lrow] = av[0][j];
+      As[lk + j][lrow + 64] = av[1][j];
+      Bs[lk + j][lrow] = wv[j];
+    }
+    __syncthreads();
+    if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tr]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][tr + 64]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tc]);
+      const float a[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[TN] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
   }
   // ---- epilogue
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int64_t m = m0 + tr + i;
+    const int64_t m = m0 + tr + (i & 3) + 64 * (i >> 2);
     if (m >= M) continue;
     const int b = (int)(m / p.T_out);
 #pragma unroll
