@@ -12,11 +12,11 @@ timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/$
 fi
 if [ -n "$NCU" ]; then
   # launch list of a short bench run (per-launch gpu time; shares must agree with bench.py's live event timing)
-  timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2500 -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --utterances 64 --steps 1 --warmup 1 --no-cpu-baseline --no-profile > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu_list=$?"
   python tools/ncu_summarize.py gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_summary.txt 2>&1; rm -f gpurun_out/${TAG}_launches.csv
   # full captures, two launches per kernel family of one velocity evaluation + codec decode
-  for K in tapgemm_tc2_kernel dwconv_tma_kernel ln_mod_kernel gn_stream_kernel act1d_kernel; do
+  for K in tapgemm_tc2_kernel dwconv_tma_kernel ln_mod_bf16_kernel gn_stream_kernel act1d_kernel; do
     SKIP=2; [ "$K" = tapgemm_tc2_kernel ] && SKIP=3
     PB=32 PL=1200 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"$K" --launch-skip $SKIP -c 3 \
       -o gpurun_out/${TAG}_ncu_$K python tools/kernels_probe.py > gpurun_out/${TAG}_ncu_$K.log 2>&1; echo "ncu $K=$?"
