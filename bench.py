@@ -363,6 +363,14 @@ def main():
             kernels[name] = {"launches": r["launches"], "ms": round(r["ms"], 3), "share_of_step": round(r["ms"] / prof_wall, 4),
                              "bound": "tensor" if tensor_bound else "hbm", "achieved": round(ach, 2),
                              "unit": "TFLOP/s" if tensor_bound else "GB/s", "frac": round(ach / peak, 4)}
+            if name in ("dwconv31_stats", "snake_act1d") and r["flops"] > 0:
+                # these two are bound by the fp32 FMA pipes before HBM: 31 / ~26 FMA per element.
+                # fp32 peak = SMs x 128 lanes x 2 FLOP x the SM clock measured during the run
+                sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                fpeak = torch.cuda.get_device_properties(device).multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
+                fach = r["flops"] / (r["ms"] * 1e-3) / 1e12
+                kernels[name].update({"fp32_tflops": round(fach, 2), "fp32_peak_tflops": round(fpeak, 2),
+                                      "fp32_frac": round(fach / fpeak, 4), "binding": "fp32 FMA pipe"})
         top = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
         k = kernels[top]
         traffic = None
