@@ -115,6 +115,14 @@ def test_no_cpu_fallback(model):
         model.prior_generator.pva.sample(torch.zeros(1, 3, 192), torch.tensor([3]), torch.zeros(1, 3, dtype=torch.bool))
 
 
+def test_sample_batches_has_no_cpu_fallback(model):
+    """the pipelined metadata entry point (Flamed.sample_batches) fails loudly on a CPU model, like sample_batch"""
+    b = dict(phonemes=torch.ones(1, 4, dtype=torch.long), src_lens=torch.tensor([4]),
+             prompts=torch.zeros(1, 6, 8, dtype=torch.long), timbres=torch.zeros(1, 256))
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        model.sample_batches([b], nsteps_durgen=2, nsteps_denoiser=2)
+
+
 def test_c_abi_exports_every_declared_symbol():
     """libflamed_b200.so loads and exports each function include/flamed_b200.h declares (no compute)."""
     from flamed_tts_b200 import _lib
