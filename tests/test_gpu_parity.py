@@ -122,6 +122,15 @@ def test_tapgemm_cta_pair_kernel_vs_torch_and_first_generation():
     assert "gen1 vs gen2 max-abs 0.000e+00" in r.stdout
 
 
+def test_tiny_and_ragged_shapes_bf16():
+    """L = 2 ... 129 frames, B = 1 ... 5 through the bf16 denoiser velocity and the codec decoder (tiles smaller than a
+    CTA pair, chunks shorter than the conv window, dummy half-tiles): <= 2e-2 / 5e-2 of the oracle, no NaNs"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "edge_shapes.py")], capture_output=True, text=True,
+                       timeout=240)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "ALL OK" in r.stdout
+
+
 _DW_SCRIPT = r"""
 import os, sys
 sys.path.insert(0, %r)
