@@ -67,8 +67,27 @@ class PriorGenerator(nn.Module):
         return self.pva.sample(enc, src_lens, src_mask, nfe=nfe, temperature=temperature)
 
     @torch.inference_mode()
-    def decode_priors(self, x, tgt_lens, prompts, prompts_len, bf16=False):
-        """length-regulated encoder output (B,L,192) -> (embs, logits, tgt_mask); prior_generator.py:162-181"""
+    def front_plan(self, texts, src_lens, max_src_len, nfe=4, temperature=1.0):
+        """`front` without the expand and without any host synchronisation (metadata path with re-bucketing):
+        returns (enc (B,P,192), cumsum (B,2P) i32, tgt_lens (B,) i64), all on the device."""
+        src_mask = get_mask_from_lengths(src_lens, max_src_len)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            enc = self.encoder(texts, src_mask)
+        cumsum, tgt_lens = self.pva.sample_plan(enc, src_lens, src_mask, nfe=nfe, temperature=temperature)
+        return enc.float().contiguous(), cumsum, tgt_lens
+
+    @torch.inference_mode()
+    def logits_from(self, embs, tgt_mask, bf16=False):
+        """the `head` projection of prior_generator.py:179-181 on its own: (B,6,L,384) -> (B,1025,6,L).  The sampling
+        path never reads the logits, so Flamed.sample_batch evaluates this lazily (7.5 GB at B=256)."""
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16 and embs.is_cuda):
+            logits = self.head(embs) * (~tgt_mask)[:, None, :, None]
+        return logits.float().permute(0, 3, 1, 2).contiguous()
+
+    @torch.inference_mode()
+    def decode_priors(self, x, tgt_lens, prompts, prompts_len, bf16=False, want_logits=True):
+        """length-regulated encoder output (B,L,192) -> (embs, logits, tgt_mask); prior_generator.py:162-181.
+        want_logits=False returns None for the logits (see logits_from)."""
         fast = bf16 and x.is_cuda and os.environ.get("FLAMED_B200_FFT", "kernels") != "torch"
         self.shared_decoder.b200 = fast
         for d in self.prior_decoder:
@@ -86,5 +105,5 @@ class PriorGenerator(nn.Module):
                 x = x[:, prompts_len:]
                 hiddens.append(x)
             out = torch.stack(hiddens, dim=1).float()             # (B, 6, L, 384)
-            logits = self.head(out) * (~tgt_mask)[:, None, :, None]
-        return out, logits.float().permute(0, 3, 1, 2).contiguous(), tgt_mask
+        logits = self.logits_from(out, tgt_mask, bf16) if want_logits else None
+        return out, logits, tgt_mask

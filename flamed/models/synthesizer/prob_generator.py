@@ -110,8 +110,12 @@ class ProbGenerator(EngineOwner):
         c = eng.cond_prepare(cond, mask)
         b, l, d = c.shape
         ts = torch.linspace(0, 1, nfe + 1)
-        ndev = c.device if self.noise_device == "cuda" else "cpu"
-        noise = torch.randn((b, l, self.target_dim), device=ndev)
+        seed = 0
+        if self.noise_device == "philox":  # drawn inside the x0 kernel from a seed (documented map, flamed_b200.h)
+            noise, seed = None, int(torch.randint(0, 2 ** 62, (1,)).item())
+        else:
+            ndev = c.device if self.noise_device == "cuda" else "cpu"
+            noise = torch.randn((b, l, self.target_dim), device=ndev)
         graph = (b * l <= self.graph_max_rows) if self.use_cuda_graph == "auto" else bool(self.use_cuda_graph)
-        x = eng.sample(c, spk, noise, ts, temperature, use_graph=graph)
+        x = eng.sample(c, spk, noise, ts, temperature, use_graph=graph, seed=seed)
         return x.transpose(1, -1)

@@ -5,7 +5,7 @@ call fails, a RuntimeError is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libflamed_b200.so")
@@ -32,8 +32,13 @@ SIGNATURES = {
     "flm_ctx_destroy": (None, [c_void_p]),
     "flm_durgen_load": (c_int, [c_void_p, POINTER(flm_tensor), c_int, POINTER(c_void_p)]),
     "flm_durgen_destroy": (None, [c_void_p]),
-    "flm_durgen_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int,
-                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "flm_durgen_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p, c_int, c_float,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "flm_durgen_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p]),
+    "flm_philox_normal": (c_int, [c_void_p, c_uint64, c_int, c_int64, c_void_p, c_void_p]),
+    "flm_lr_expand_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
     "flm_lr_plan": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                             POINTER(c_int64), c_void_p]),
     "flm_lr_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -41,8 +46,8 @@ SIGNATURES = {
                                   POINTER(c_void_p)]),
     "flm_denoiser_destroy": (None, [c_void_p]),
     "flm_cond_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "flm_denoiser_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
-                                    c_void_p, c_int, c_void_p]),
+    "flm_denoiser_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p, c_int, c_int, c_int,
+                                    c_float, c_void_p, c_int, c_void_p]),
     "flm_denoiser_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p]),
     "flm_denoiser_launches_per_step": (c_int, [c_void_p]),
     "flm_codec_dec_load": (c_int, [c_void_p, POINTER(flm_tensor), c_int, c_int, POINTER(c_void_p)]),
@@ -53,6 +58,11 @@ SIGNATURES = {
     "flm_codec_enc_destroy": (None, [c_void_p]),
     "flm_codec_enc_frames": (c_int64, [c_void_p, c_int64]),
     "flm_codec_encode": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "flm_wav_to_pcm16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "flm_comm_unique_id": (c_int, [c_void_p]),
+    "flm_comm_create": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "flm_comm_destroy": (None, [c_void_p]),
+    "flm_gather_wav": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64), c_int, c_void_p]),
     "flm_profile_enable": (c_int, [c_void_p, c_int]),
     "flm_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), c_int]),
     "flm_profile_class_name": (c_char_p, [c_int]),

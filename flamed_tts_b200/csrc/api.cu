@@ -7,8 +7,9 @@
 
 using namespace flm;
 
-static thread_local std::string g_last_error;
-namespace flm { unsigned long long g_launch_count = 0; }
+thread_local std::string flm_g_last_error;  // shared with comm.cu
+#define g_last_error flm_g_last_error
+namespace flm { std::atomic<unsigned long long> g_launch_count{0}; }
 
 #define FLM_API_BEGIN try {
 #define FLM_API_END                          \
@@ -25,7 +26,7 @@ namespace flm { unsigned long long g_launch_count = 0; }
 
 extern "C" const char* flm_last_error(void) { return g_last_error.c_str(); }
 extern "C" int flm_version(void) { return 100; }
-extern "C" unsigned long long flm_launch_count(void) { return flm::g_launch_count; }
+extern "C" unsigned long long flm_launch_count(void) { return flm::g_launch_count.load(); }
 
 // ===================================================================================== context
 extern "C" int flm_ctx_create(int device, flm_ctx** out) {
@@ -36,7 +37,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
   if (e != cudaSuccess || count == 0)
     throw Error(FLM_ERR_CUDA, "no CUDA device: flamed_b200 has no CPU fallback (needs an sm_100 GPU)");
   FLM_REQUIRE(device >= 0 && device < count, "bad device index");
-  FLM_CUDA(cudaSetDevice(device));
+  DeviceGuard dguard(device);
   cudaDeviceProp prop;
   FLM_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -60,7 +61,6 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
 extern "C" void flm_ctx_destroy(flm_ctx* ctx) { delete ctx; }
 
 static inline cudaStream_t S(flm_stream s) { return static_cast<cudaStream_t>(s); }
-static void set_device(flm_ctx* ctx) { FLM_CUDA(cudaSetDevice(ctx->device)); }
 
 static std::vector<float> replicate(const std::vector<float>& v, int times) {
   std::vector<float> o;
@@ -82,7 +82,7 @@ struct DurNet {
 
 struct flm_durgen : Engine {
   DurNet net[2];
-  DevBuf enc_s, noise_s[2], mask_s, ts_s, out_s[2];
+  DevBuf enc_s, noise_s[2], mask_s, ts_s, out_s[2], seed_s;
   GraphCache graphs;
   flm_durgen(flm_ctx* c) : Engine(c, FLM_F32) {}
 
@@ -120,34 +120,71 @@ struct flm_durgen : Engine {
     n.bl = store.upload(wm.vec(p + ".linear_layer.bias", {1}));
   }
 
-  void body(int B, int P, int nfe, float temperature, cudaStream_t s) {
+  // one velocity evaluation of generator g at time-table row i, accumulated into xt: xt += dt * v
+  void velocity(int g, int B, int P, int i, float dt, cudaStream_t s) {
+    trunk(g, B, P, i, s);
+    DurNet& n = net[g];
+    launch_durgen_head(n.r2.as<float>(), (int64_t)B * P, n.F, n.ln2w, n.ln2b, n.wl, n.bl, mask_s.as<uint8_t>(), dt,
+                       n.xt.as<float>(), s);
+  }
+  // everything of ProbabilisticModule.forward up to the second conv (pva.py:222-233): r2 = conv2(LN(relu(conv1(...))))
+  void trunk(int g, int B, int P, int i, cudaStream_t s) {
+    const int64_t rows = (int64_t)B * P;
+    DurNet& n = net[g];
+    launch_durgen_input(n.encp.as<float>(), n.xt.as<float>(), n.w0, n.temb.as<float>() + (int64_t)i * n.D, rows, n.D,
+                        n.a0.as<float>(), s);
+    gemm(problem(n.c1, n.a0.p, n.D, B, P, P, n.r1.p, n.F, 0, EPI_NONE), n.c1, false, s);
+    LnMod ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = n.r1.p; ln.ldx = n.F; ln.y = n.l1.p; ln.ldy = n.F; ln.y_bf16 = 0;
+    ln.w = n.ln1w; ln.b = n.ln1b; ln.eps = 1e-5f; ln.rows = rows; ln.rows_per_batch = P; ln.C = n.F;
+    ln.relu_in = 1;
+    launch_ln_mod(ln, s);
+    gemm(problem(n.c2, n.l1.p, n.F, B, P, P, n.r2.p, n.F, 0, EPI_NONE), n.c2, false, s);
+  }
+  void prologue(int g, int B, int P, int nfe, cudaStream_t s) {
+    DurNet& n = net[g];
+    gemm(problem(n.encproj, enc_s.p, n.D, B, P, P, n.encp.p, n.D, 0, EPI_NONE), n.encproj, false, s);
+    launch_sinusoidal_pos_emb(ts_s.as<float>(), nfe, n.D, n.semb.as<float>(), s);
+    gemm(problem(n.te1, n.semb.p, n.D, 1, nfe, nfe, n.teh.p, n.te1.N, 0, EPI_SILU), n.te1, false, s);
+    gemm(problem(n.te3, n.teh.p, n.te1.N, 1, nfe, nfe, n.temb.p, n.D, 0, EPI_NONE), n.te3, false, s);
+  }
+  bool ensure(int B, int P, int nfe) {
+    const int64_t rows = (int64_t)B * P;
+    bool moved = false;
+    moved |= enc_s.ensure(rows * net[0].D * 4);
+    moved |= mask_s.ensure(rows);
+    moved |= ts_s.ensure((nfe + 1) * 4);
+    moved |= seed_s.ensure(8);
+    for (int g = 0; g < 2; ++g) {
+      DurNet& n = net[g];
+      moved |= noise_s[g].ensure(rows * 4);
+      moved |= out_s[g].ensure(rows * 4);
+      moved |= n.encp.ensure(rows * n.D * 4);
+      moved |= n.semb.ensure((size_t)nfe * n.D * 4);
+      moved |= n.teh.ensure((size_t)nfe * n.te1.N * 4);
+      moved |= n.temb.ensure((size_t)nfe * n.D * 4);
+      moved |= n.a0.ensure(rows * n.D * 4);
+      moved |= n.r1.ensure(rows * n.F * 4);
+      moved |= n.l1.ensure(rows * n.F * 4);
+      moved |= n.r2.ensure(rows * n.F * 4);
+      moved |= n.xt.ensure(rows * 4);
+    }
+    if (moved) graphs.clear();
+    return moved;
+  }
+
+  void body(int B, int P, int nfe, float temperature, bool philox, cudaStream_t s) {
     const int64_t rows = (int64_t)B * P;
     const float dt = (float)(1.0 / nfe);
     for (int g = 0; g < 2; ++g) {
       DurNet& n = net[g];
-      launch_scale(noise_s[g].as<float>(), temperature, rows, n.xt.as<float>(), s);
-      gemm(problem(n.encproj, enc_s.p, n.D, B, P, P, n.encp.p, n.D, 0, EPI_NONE), n.encproj, false, s);
-      launch_sinusoidal_pos_emb(ts_s.as<float>(), nfe, n.D, n.semb.as<float>(), s);
-      gemm(problem(n.te1, n.semb.p, n.D, 1, nfe, nfe, n.teh.p, n.te1.N, 0, EPI_SILU), n.te1, false, s);
-      gemm(problem(n.te3, n.teh.p, n.te1.N, 1, nfe, nfe, n.temb.p, n.D, 0, EPI_NONE), n.te3, false, s);
+      if (philox) launch_philox_normal(seed_s.as<uint64_t>(), (uint32_t)g, temperature, nullptr, rows, n.xt.as<float>(), s);
+      else launch_scale(noise_s[g].as<float>(), temperature, rows, n.xt.as<float>(), s);
+      prologue(g, B, P, nfe, s);
     }
-    for (int i = 0; i < nfe; ++i) {
-      for (int g = 0; g < 2; ++g) {
-        DurNet& n = net[g];
-        launch_durgen_input(n.encp.as<float>(), n.xt.as<float>(), n.w0, n.temb.as<float>() + (int64_t)i * n.D, rows,
-                            n.D, n.a0.as<float>(), s);
-        gemm(problem(n.c1, n.a0.p, n.D, B, P, P, n.r1.p, n.F, 0, EPI_NONE), n.c1, false, s);
-        LnMod ln;
-        memset(&ln, 0, sizeof(ln));
-        ln.x = n.r1.p; ln.ldx = n.F; ln.y = n.l1.p; ln.ldy = n.F; ln.y_bf16 = 0;
-        ln.w = n.ln1w; ln.b = n.ln1b; ln.eps = 1e-5f; ln.rows = rows; ln.rows_per_batch = P; ln.C = n.F;
-        ln.relu_in = 1;
-        launch_ln_mod(ln, s);
-        gemm(problem(n.c2, n.l1.p, n.F, B, P, P, n.r2.p, n.F, 0, EPI_NONE), n.c2, false, s);
-        launch_durgen_head(n.r2.as<float>(), rows, n.F, n.ln2w, n.ln2b, n.wl, n.bl, mask_s.as<uint8_t>(), dt,
-                           n.xt.as<float>(), s);
-      }
-    }
+    for (int i = 0; i < nfe; ++i)
+      for (int g = 0; g < 2; ++g) velocity(g, B, P, i, dt, s);
     for (int g = 0; g < 2; ++g) launch_duration_round(net[g].xt.as<float>(), rows, out_s[g].as<float>(), s);
   }
 };
@@ -155,7 +192,7 @@ struct flm_durgen : Engine {
 extern "C" int flm_durgen_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_durgen** out) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && weights && out, "null argument");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   WeightMap wm(weights, n);
   std::unique_ptr<flm_durgen> h(new flm_durgen(ctx));
   h->load_net(wm, "duration_generator", h->net[0]);
@@ -166,44 +203,32 @@ extern "C" int flm_durgen_load(flm_ctx* ctx, const flm_tensor* weights, int n, f
 extern "C" void flm_durgen_destroy(flm_durgen* h) { delete h; }
 
 extern "C" int flm_durgen_sample(flm_durgen* h, const float* enc, const float* noise_dur, const float* noise_sil,
-                                 const uint8_t* src_mask, const float* ts_host, int nfe, float temperature, int B, int P,
-                                 float* out_phone, float* out_sil, float* out_dur_t, float* out_sil_t,
+                                 uint64_t seed, const uint8_t* src_mask, const float* ts_host, int nfe, float temperature,
+                                 int B, int P, float* out_phone, float* out_sil, float* out_dur_t, float* out_sil_t,
                                  flm_stream stream) {
   FLM_API_BEGIN
-  FLM_REQUIRE(h && enc && noise_dur && noise_sil && src_mask && ts_host && out_phone && out_sil, "null argument");
+  FLM_REQUIRE(h && enc && src_mask && ts_host && out_phone && out_sil, "null argument");
+  FLM_REQUIRE((noise_dur == nullptr) == (noise_sil == nullptr), "noise_dur and noise_sil must both be given or both be NULL");
   FLM_REQUIRE(nfe >= 1 && B >= 0 && P >= 1, "bad sizes");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   if (B == 0) return FLM_OK;
   cudaStream_t s = S(stream);
   const int64_t rows = (int64_t)B * P;
-  bool moved = false;
-  moved |= h->enc_s.ensure(rows * h->net[0].D * 4);
-  moved |= h->mask_s.ensure(rows);
-  moved |= h->ts_s.ensure((nfe + 1) * 4);
-  for (int g = 0; g < 2; ++g) {
-    DurNet& n = h->net[g];
-    moved |= h->noise_s[g].ensure(rows * 4);
-    moved |= h->out_s[g].ensure(rows * 4);
-    moved |= n.encp.ensure(rows * n.D * 4);
-    moved |= n.semb.ensure((size_t)nfe * n.D * 4);
-    moved |= n.teh.ensure((size_t)nfe * n.te1.N * 4);
-    moved |= n.temb.ensure((size_t)nfe * n.D * 4);
-    moved |= n.a0.ensure(rows * n.D * 4);
-    moved |= n.r1.ensure(rows * n.F * 4);
-    moved |= n.l1.ensure(rows * n.F * 4);
-    moved |= n.r2.ensure(rows * n.F * 4);
-    moved |= n.xt.ensure(rows * 4);
-  }
-  if (moved) h->graphs.clear();
+  const bool philox = noise_dur == nullptr;
+  h->ensure(B, P, nfe);
   FLM_CUDA(cudaMemcpyAsync(h->enc_s.p, enc, rows * h->net[0].D * 4, cudaMemcpyDeviceToDevice, s));
-  FLM_CUDA(cudaMemcpyAsync(h->noise_s[0].p, noise_dur, rows * 4, cudaMemcpyDeviceToDevice, s));
-  FLM_CUDA(cudaMemcpyAsync(h->noise_s[1].p, noise_sil, rows * 4, cudaMemcpyDeviceToDevice, s));
+  if (philox) {
+    FLM_CUDA(cudaMemcpyAsync(h->seed_s.p, &seed, 8, cudaMemcpyHostToDevice, s));
+  } else {
+    FLM_CUDA(cudaMemcpyAsync(h->noise_s[0].p, noise_dur, rows * 4, cudaMemcpyDeviceToDevice, s));
+    FLM_CUDA(cudaMemcpyAsync(h->noise_s[1].p, noise_sil, rows * 4, cudaMemcpyDeviceToDevice, s));
+  }
   FLM_CUDA(cudaMemcpyAsync(h->mask_s.p, src_mask, rows, cudaMemcpyDeviceToDevice, s));
   FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts_host, (nfe + 1) * 4, cudaMemcpyHostToDevice, s));
   int tbits;
   memcpy(&tbits, &temperature, 4);
-  h->graphs.run(std::make_tuple(B, P, nfe, tbits), s,
-                [&](cudaStream_t cs) { h->body(B, P, nfe, temperature, cs); });
+  h->graphs.run(std::make_tuple(B, P, philox ? -nfe : nfe, tbits), s,
+                [&](cudaStream_t cs) { h->body(B, P, nfe, temperature, philox, cs); });
   FLM_CUDA(cudaMemcpyAsync(out_phone, h->out_s[0].p, rows * 4, cudaMemcpyDeviceToDevice, s));
   FLM_CUDA(cudaMemcpyAsync(out_sil, h->out_s[1].p, rows * 4, cudaMemcpyDeviceToDevice, s));
   if (out_dur_t) FLM_CUDA(cudaMemcpyAsync(out_dur_t, h->net[0].xt.p, rows * 4, cudaMemcpyDeviceToDevice, s));
@@ -211,15 +236,46 @@ extern "C" int flm_durgen_sample(flm_durgen* h, const float* enc, const float* n
   FLM_API_END
 }
 
+// one vector-field evaluation v = ProbabilisticModule.forward(x, enc, t, mask) (pva.py:221-238) of generator
+// `which` (0 duration, 1 silence): the same kernels as one step of the loop, with x as the state and dt = 1
+extern "C" int flm_durgen_forward(flm_durgen* h, int which, const float* x, const float* enc, float t,
+                                  const uint8_t* src_mask, int B, int P, float* out_v, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && x && enc && out_v, "null argument");
+  FLM_REQUIRE(which == 0 || which == 1, "which must be 0 (duration) or 1 (silence)");
+  FLM_REQUIRE(B >= 0 && P >= 1, "bad sizes");
+  DeviceGuard dguard(h->ctx->device);
+  if (B == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int64_t rows = (int64_t)B * P;
+  h->ensure(B, P, 1);
+  DurNet& n = h->net[which];
+  const float ts[2] = {t, 1.0f};
+  FLM_CUDA(cudaMemcpyAsync(h->enc_s.p, enc, rows * n.D * 4, cudaMemcpyDeviceToDevice, s));
+  if (src_mask) FLM_CUDA(cudaMemcpyAsync(h->mask_s.p, src_mask, rows, cudaMemcpyDeviceToDevice, s));
+  else FLM_CUDA(cudaMemsetAsync(h->mask_s.p, 0, rows, s));
+  FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts, 8, cudaMemcpyHostToDevice, s));
+  FLM_CUDA(cudaMemcpyAsync(n.xt.p, x, rows * 4, cudaMemcpyDeviceToDevice, s));
+  h->prologue(which, B, P, 1, s);
+  h->trunk(which, B, P, 0, s);
+  // the head accumulates xt += dt * v: on a zero state with dt = 1 that is exactly v
+  FLM_CUDA(cudaMemsetAsync(n.xt.p, 0, rows * 4, s));
+  launch_durgen_head(n.r2.as<float>(), rows, n.F, n.ln2w, n.ln2b, n.wl, n.bl, h->mask_s.as<uint8_t>(), 1.0f,
+                     n.xt.as<float>(), s);
+  FLM_CUDA(cudaMemcpyAsync(out_v, n.xt.p, rows * 4, cudaMemcpyDeviceToDevice, s));
+  FLM_API_END
+}
+
 // ===================================================================================== length regulator
 extern "C" int flm_lr_plan(flm_ctx* ctx, const float* phone_dur, const float* sil_dur, const int64_t* src_lens, int B,
                            int P, int32_t* out_cumsum, int64_t* out_tgt_len, int64_t* out_tmax_host, flm_stream stream) {
   FLM_API_BEGIN
-  FLM_REQUIRE(ctx && phone_dur && sil_dur && src_lens && out_cumsum && out_tgt_len && out_tmax_host, "null argument");
-  set_device(ctx);
-  *out_tmax_host = 0;
+  FLM_REQUIRE(ctx && phone_dur && sil_dur && src_lens && out_cumsum && out_tgt_len, "null argument");
+  DeviceGuard dguard(ctx->device);
+  if (out_tmax_host) *out_tmax_host = 0;
   if (B == 0) return FLM_OK;
   launch_lr_plan(phone_dur, sil_dur, src_lens, B, P, out_cumsum, out_tgt_len, S(stream));
+  if (!out_tmax_host) return FLM_OK;  // asynchronous form: the caller reads tgt_len later (batched re-bucketing)
   std::vector<int64_t> tl(B);
   FLM_CUDA(cudaMemcpyAsync(tl.data(), out_tgt_len, (size_t)B * 8, cudaMemcpyDeviceToHost, S(stream)));
   FLM_CUDA(cudaStreamSynchronize(S(stream)));  // the one documented sync (reference: pva.py:158 .tolist())
@@ -233,8 +289,18 @@ extern "C" int flm_lr_expand(flm_ctx* ctx, const float* x, const int32_t* cumsum
                              float* out, int32_t* out_index, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && x && cumsum && out, "null argument");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   launch_lr_expand(x, cumsum, B, P, H, Tmax, out, out_index, S(stream));
+  FLM_API_END
+}
+
+extern "C" int flm_lr_expand_gather(flm_ctx* ctx, const float* const* x_rows, const int32_t* const* cumsums,
+                                    const int32_t* P_per_sample, int B, int H, int Tmax, float* out, int32_t* out_index,
+                                    flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && x_rows && cumsums && P_per_sample && out, "null argument");
+  DeviceGuard dguard(ctx->device);
+  launch_lr_expand_gather(x_rows, cumsums, P_per_sample, B, H, Tmax, out, out_index, S(stream));
   FLM_API_END
 }
 
@@ -266,6 +332,7 @@ struct flm_denoiser : Engine {
   std::vector<Stage> stages;
   Layer proj_out;
   // buffers
+  DevBuf seed_s;
   DevBuf cond_s, spk_s, noise_s, ts_s, x, xb, h, bufU, bufD, bufG, bufA, part, gsc, gof, gctr, ada, sbuf, temb, tfreq, teh,
       cvec, vout;
   DevBuf c_prior, c_mask, c_xq, c_xm, c_h, c_part, c_sc, c_of, c_out;
@@ -449,7 +516,7 @@ struct flm_denoiser : Engine {
     const size_t e = esize();
     bool moved = false;
     moved |= cond_s.ensure(M * D * 4); moved |= spk_s.ensure((size_t)B * cfg.spk_dim * 4);
-    moved |= noise_s.ensure(M * D * 4); moved |= ts_s.ensure((size_t)(nfe + 1) * 4);
+    moved |= noise_s.ensure(M * D * 4); moved |= ts_s.ensure((size_t)(nfe + 1) * 4); moved |= seed_s.ensure(8);
     moved |= x.ensure(M * D * 4); moved |= xb.ensure(M * D * 2); moved |= vout.ensure(M * D * 4);
     moved |= h.ensure(M * H * 4);
     moved |= bufU.ensure(M * H * e); moved |= bufD.ensure(M * H * e); moved |= bufG.ensure(M * H * e);
@@ -475,7 +542,7 @@ extern "C" int flm_denoiser_load(flm_ctx* ctx, const flm_tensor* weights, int n,
   FLM_REQUIRE(mode == FLM_F32 || mode == FLM_BF16, "bad mode");
   FLM_REQUIRE(cfg->hidden_dim % 256 == 0 && cfg->hidden_dim <= 1024, "hidden_dim must be a multiple of 256, <= 1024");
   FLM_REQUIRE(cfg->target_dim % 64 == 0, "target_dim must be a multiple of 64");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   WeightMap wm(weights, n);
   std::unique_ptr<flm_denoiser> h(new flm_denoiser(ctx, mode));
   h->cfg = *cfg;
@@ -496,7 +563,7 @@ extern "C" int flm_cond_prepare(flm_denoiser* h, const float* prior_embs, const 
                                 float* out_cond, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(h && prior_embs && mask && out_cond, "null argument");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   if (B == 0 || L == 0) return FLM_OK;
   cudaStream_t s = S(stream);
   const int Q = h->cfg.n_quantizers, CD = h->cfg.cond_dim;
@@ -542,31 +609,36 @@ extern "C" int flm_cond_prepare(flm_denoiser* h, const float* prior_embs, const 
 }
 
 extern "C" int flm_denoiser_sample(flm_denoiser* h, const float* cond, const float* spk, const float* noise,
-                                   const float* ts_host, int B, int L, int nfe, float temperature, float* out_latents,
-                                   int use_graph, flm_stream stream) {
+                                   uint64_t seed, const float* ts_host, int B, int L, int nfe, float temperature,
+                                   float* out_latents, int use_graph, flm_stream stream) {
   FLM_API_BEGIN
-  FLM_REQUIRE(h && cond && spk && noise && ts_host && out_latents, "null argument");
+  FLM_REQUIRE(h && cond && spk && ts_host && out_latents, "null argument");
   FLM_REQUIRE(nfe >= 1, "nfe must be >= 1");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   if (B == 0 || L == 0) return FLM_OK;
   cudaStream_t s = S(stream);
   const int64_t M = (int64_t)B * L;
+  const bool philox = noise == nullptr;  // x0 = temperature * N(0,1) + cond drawn in the init kernel (documented map)
   h->ensure(B, L, nfe);
   FLM_CUDA(cudaMemcpyAsync(h->cond_s.p, cond, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
   FLM_CUDA(cudaMemcpyAsync(h->spk_s.p, spk, (size_t)B * h->cfg.spk_dim * 4, cudaMemcpyDeviceToDevice, s));
-  FLM_CUDA(cudaMemcpyAsync(h->noise_s.p, noise, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
+  if (philox) FLM_CUDA(cudaMemcpyAsync(h->seed_s.p, &seed, 8, cudaMemcpyHostToDevice, s));
+  else FLM_CUDA(cudaMemcpyAsync(h->noise_s.p, noise, M * h->D * 4, cudaMemcpyDeviceToDevice, s));
   FLM_CUDA(cudaMemcpyAsync(h->ts_s.p, ts_host, (size_t)(nfe + 1) * 4, cudaMemcpyHostToDevice, s));
   const float dt = (float)(1.0 / nfe);
   auto body = [&](cudaStream_t cs) {
     h->xb_fresh = false;
     h->modulation_table(B, nfe, cs);
-    launch_noise_init(h->noise_s.as<float>(), h->cond_s.as<float>(), temperature, M * h->D, h->x.as<float>(), cs);
+    if (philox)
+      launch_philox_normal(h->seed_s.as<uint64_t>(), 2u, temperature, h->cond_s.as<float>(), M * h->D, h->x.as<float>(), cs);
+    else
+      launch_noise_init(h->noise_s.as<float>(), h->cond_s.as<float>(), temperature, M * h->D, h->x.as<float>(), cs);
     for (int i = 0; i < nfe; ++i) h->step(B, L, i, h->x.as<float>(), dt, cs);
   };
   if (use_graph) {
     int tbits;
     memcpy(&tbits, &temperature, 4);
-    h->graphs.run(std::make_tuple(B, L, nfe, tbits), s, body);
+    h->graphs.run(std::make_tuple(B, L, philox ? -nfe : nfe, tbits), s, body);
   } else {
     body(s);
   }
@@ -574,11 +646,25 @@ extern "C" int flm_denoiser_sample(flm_denoiser* h, const float* cond, const flo
   FLM_API_END
 }
 
+// the (n) standard-normal values of the documented Philox map for tensor `tensor_id` (0 duration, 1 silence, 2 latent):
+// what flm_durgen_sample / flm_denoiser_sample draw internally when their noise pointers are NULL.  For tests.
+extern "C" int flm_philox_normal(flm_ctx* ctx, uint64_t seed, int tensor_id, int64_t n, float* out, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && out && n >= 0 && tensor_id >= 0, "bad arguments");
+  DeviceGuard dguard(ctx->device);
+  DevBuf sd;
+  sd.ensure(8);
+  FLM_CUDA(cudaMemcpyAsync(sd.p, &seed, 8, cudaMemcpyHostToDevice, S(stream)));
+  launch_philox_normal(sd.as<uint64_t>(), (uint32_t)tensor_id, 1.0f, nullptr, n, out, S(stream));
+  FLM_CUDA(cudaStreamSynchronize(S(stream)));  // sd is freed on return
+  FLM_API_END
+}
+
 extern "C" int flm_denoiser_forward(flm_denoiser* h, const float* x, const float* spk, float t, int B, int L,
                                     float* out_v, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(h && x && spk && out_v, "null argument");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   if (B == 0 || L == 0) return FLM_OK;
   cudaStream_t s = S(stream);
   const int64_t M = (int64_t)B * L;
@@ -677,7 +763,7 @@ extern "C" int flm_codec_dec_load(flm_ctx* ctx, const flm_tensor* weights, int n
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && weights && out, "null argument");
   FLM_REQUIRE(mode == FLM_F32 || mode == FLM_BF16, "bad mode");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   WeightMap wm(weights, n);
   std::unique_ptr<flm_codec_dec> h(new flm_codec_dec(ctx, mode));
   const bool b = h->bf();
@@ -733,7 +819,7 @@ extern "C" int flm_codec_decode(flm_codec_dec* h, const float* latents, const fl
                                 flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(h && latents && spk && out_wav, "null argument");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   if (B == 0 || L == 0) return FLM_OK;
   cudaStream_t s = S(stream);
   const int Cin = h->conv0.K, b16 = h->bf() ? 1 : 0;
@@ -774,7 +860,7 @@ extern "C" int flm_codec_dec_activation(flm_codec_dec* h, const char* prefix, co
                                         float* y, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(h && prefix && x && y, "null argument");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   auto it = h->acts_by_name.find(prefix);
   if (it == h->acts_by_name.end()) throw Error(FLM_ERR_ARG, std::string("no activation named ") + prefix);
   FLM_REQUIRE(it->second.C == C, "channel count mismatch");
@@ -801,7 +887,7 @@ struct flm_codec_enc : Engine {
 extern "C" int flm_codec_enc_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_codec_enc** out) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && weights && out, "null argument");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   WeightMap wm(weights, n);
   std::unique_ptr<flm_codec_enc> h(new flm_codec_enc(ctx));
   const flm_tensor& w0 = wm.get("block.0.weight_v");
@@ -857,7 +943,7 @@ extern "C" int64_t flm_codec_enc_frames(flm_codec_enc* h, int64_t S_) {
 extern "C" int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S_, float* out, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(h && wav && out, "null argument");
-  set_device(h->ctx);
+  DeviceGuard dguard(h->ctx->device);
   const int64_t Tout = flm_codec_enc_frames(h, S_);
   FLM_REQUIRE(Tout > 0, "prompt too short for the encoder");
   FLM_REQUIRE(S_ < (1ll << 30), "prompt too long");
@@ -895,7 +981,7 @@ extern "C" const char* flm_profile_class_name(int kc);
 extern "C" int flm_profile_enable(flm_ctx* ctx, int on) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx != nullptr, "null ctx");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   FLM_CUDA(cudaDeviceSynchronize());
   for (auto& r : ctx->recs) { ctx->pool.push_back(r.a); ctx->pool.push_back(r.b); }
   ctx->recs.clear();
@@ -906,7 +992,7 @@ extern "C" int flm_profile_enable(flm_ctx* ctx, int on) {
 extern "C" int flm_profile_read(flm_ctx* ctx, double* out, int n_classes) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && out && n_classes >= KC_COUNT, "bad arguments (need room for 8 classes x 4 doubles)");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   FLM_CUDA(cudaDeviceSynchronize());
   for (int i = 0; i < n_classes * 4; ++i) out[i] = 0.0;
   for (auto& r : ctx->recs) {
@@ -924,7 +1010,7 @@ extern "C" int flm_profile_read(flm_ctx* ctx, double* out, int n_classes) {
 extern "C" int flm_profile_detail(flm_ctx* ctx, char* out, int cap) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && out && cap > 0, "bad arguments");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   FLM_CUDA(cudaDeviceSynchronize());
   struct Agg { double n = 0, ms = 0, flops = 0, bytes = 0; };
   std::map<std::string, Agg> agg;
@@ -959,7 +1045,7 @@ extern "C" int flm_tapgemm_test(flm_ctx* ctx, int mode, const float* A, const fl
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && A && W && out, "null argument");
   FLM_REQUIRE(epi >= 0 && epi <= EPI_RELU, "epi must be 0..3");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   cudaStream_t s = S(stream);
   TapGemm p;
   memset(&p, 0, sizeof(p));
@@ -989,7 +1075,7 @@ extern "C" int flm_tapgemm_test_bf16(flm_ctx* ctx, int gen, const void* A, const
                                      void* resid, const void* addend, const float* gate, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && A && W, "null argument");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   cudaStream_t s = S(stream);
   TapGemm p;
   memset(&p, 0, sizeof(p));
@@ -1018,7 +1104,7 @@ extern "C" int flm_conv1d_bf16(flm_ctx* ctx, const void* A, const void* W, const
   FLM_REQUIRE(ctx && A && W && out, "null argument");
   FLM_REQUIRE(epi >= EPI_NONE && epi <= EPI_RESID, "epi must be 0..4");
   FLM_REQUIRE(epi != EPI_RESID || resid != nullptr, "epi 4 needs resid");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   if ((int64_t)B * T == 0) return FLM_OK;
   TapGemm p;
   memset(&p, 0, sizeof(p));
@@ -1040,7 +1126,7 @@ extern "C" int flm_layernorm_bf16(flm_ctx* ctx, const void* x, const float* w, c
                                   int C, const uint8_t* zero_rows, void* y, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && x && y, "null argument");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   if (rows == 0) return FLM_OK;
   LnMod ln;
   memset(&ln, 0, sizeof(ln));
@@ -1058,7 +1144,7 @@ extern "C" int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, in
                                  int out_bf16, int reps, float* out_ms, flm_stream stream) {
   FLM_API_BEGIN
   FLM_REQUIRE(ctx && out_ms && reps > 0, "bad arguments");
-  set_device(ctx);
+  DeviceGuard dguard(ctx->device);
   cudaStream_t s = S(stream);
   const size_t e = mode == FLM_BF16 ? 2 : 4;
   const int64_t M = (int64_t)B * T;

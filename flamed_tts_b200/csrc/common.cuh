@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 
@@ -32,11 +33,11 @@ struct Error : std::runtime_error {
   } while (0)
 
 // every kernel launcher ends with this: checks the launch and counts it (flm_launch_count)
-extern unsigned long long g_launch_count;
-#define FLM_LAUNCH_CHECK()          \
-  do {                              \
-    ++flm::g_launch_count;          \
-    FLM_CUDA(cudaGetLastError());   \
+extern std::atomic<unsigned long long> g_launch_count;
+#define FLM_LAUNCH_CHECK()                                          \
+  do {                                                              \
+    flm::g_launch_count.fetch_add(1, std::memory_order_relaxed);    \
+    FLM_CUDA(cudaGetLastError());                                   \
   } while (0)
 
 // ---- element access in storage type T (float or bf16), arithmetic always fp32

@@ -248,28 +248,69 @@ struct Engine {
   }
 };
 
-// CUDA-graph cache: body(stream) is captured once per key on a private stream (capture is not
-// allowed on the legacy default stream, which is what torch hands us by default) and the
-// instantiated graph is then launched on the caller's stream.
+// restores the caller's current CUDA device when an API call returns (the library switches to the handle's device)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    FLM_CUDA(cudaGetDevice(&prev));
+    if (prev != device) FLM_CUDA(cudaSetDevice(device));
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// CUDA-graph cache: body(stream) is captured on a private stream (capture is not allowed on the legacy default
+// stream, which is what torch hands us by default) and the instantiated graph is then launched on the caller's
+// stream.  Keys are data dependent (B, P | L, nfe, temperature bits), so the cache is bounded: a key is launched
+// directly the first time it is seen and only captured + instantiated when it comes back (one-shot shapes never pay
+// for a capture), and at most `capacity` executables are kept, least recently used first out.
 struct GraphCache {
-  std::map<std::tuple<int, int, int, int>, cudaGraphExec_t> execs;
-  std::map<cudaGraphExec_t, unsigned long long> kernels_in;  // kernel nodes per graph (launch accounting)
+  typedef std::tuple<int, int, int, int> Key;
+  struct Entry { cudaGraphExec_t exec; unsigned long long kernels; unsigned long long stamp; };
+  std::map<Key, Entry> execs;
+  std::map<Key, unsigned long long> seen;  // keys launched directly so far -> last-use stamp (bounded below)
+  size_t capacity = 8;
+  unsigned long long clock = 0;
   cudaStream_t capture_stream = nullptr;
   ~GraphCache() {
     clear();
     if (capture_stream) cudaStreamDestroy(capture_stream);
   }
   void clear() {
-    for (auto& kv : execs) cudaGraphExecDestroy(kv.second);
+    for (auto& kv : execs) cudaGraphExecDestroy(kv.second.exec);
     execs.clear();
-    kernels_in.clear();
+    seen.clear();
   }
-  void run(std::tuple<int, int, int, int> key, cudaStream_t stream, const std::function<void(cudaStream_t)>& body) {
+  size_t size() const { return execs.size(); }
+  void run(Key key, cudaStream_t stream, const std::function<void(cudaStream_t)>& body) {
+    ++clock;
     auto it = execs.find(key);
     if (it == execs.end()) {
+      auto sit = seen.find(key);
+      if (sit == seen.end()) {  // first sighting: direct launches, remember the key
+        if (seen.size() >= 4 * capacity) {
+          auto old = seen.begin();
+          for (auto j = seen.begin(); j != seen.end(); ++j)
+            if (j->second < old->second) old = j;
+          seen.erase(old);
+        }
+        seen[key] = clock;
+        body(stream);
+        return;
+      }
+      seen.erase(sit);
+      if (execs.size() >= capacity) {  // evict the least recently used executable
+        auto old = execs.begin();
+        for (auto j = execs.begin(); j != execs.end(); ++j)
+          if (j->second.stamp < old->second.stamp) old = j;
+        cudaGraphExecDestroy(old->second.exec);
+        execs.erase(old);
+      }
       if (!capture_stream) FLM_CUDA(cudaStreamCreateWithFlags(&capture_stream, cudaStreamNonBlocking));
       cudaGraph_t graph = nullptr;
-      const unsigned long long before = g_launch_count;
+      const unsigned long long before = g_launch_count.load();
       FLM_CUDA(cudaStreamBeginCapture(capture_stream, cudaStreamCaptureModeRelaxed));
       try {
         body(capture_stream);
@@ -284,12 +325,16 @@ struct GraphCache {
       cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
       cudaGraphDestroy(graph);
       FLM_CUDA(e);
-      it = execs.emplace(key, exec).first;
-      kernels_in[exec] = g_launch_count - before;
-      g_launch_count = before;  // captured, not launched: counted at each replay below
+      Entry en;
+      en.exec = exec;
+      en.kernels = g_launch_count.load() - before;
+      en.stamp = clock;
+      g_launch_count.fetch_sub(en.kernels);  // captured, not launched: counted at each replay below
+      it = execs.emplace(key, en).first;
     }
-    g_launch_count += kernels_in[it->second];
-    FLM_CUDA(cudaGraphLaunch(it->second, stream));
+    it->second.stamp = clock;
+    g_launch_count.fetch_add(it->second.kernels);
+    FLM_CUDA(cudaGraphLaunch(it->second.exec, stream));
   }
 };
 

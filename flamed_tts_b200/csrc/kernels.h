@@ -99,6 +99,10 @@ void launch_silu_sum(const float* temb, const float* cvec, int nfe, int B, int C
                      cudaStream_t stream);
 // x0 = noise * temperature + cond  (prob_generator.py:440); also writes a bf16 copy if xb != null
 void launch_noise_init(const float* noise, const float* cond, float temperature, int64_t n, float* x, cudaStream_t s);
+// out[i] = N(0,1)[i] * scale (+ add[i]): Philox4x32-10 + Box-Muller, seed read from device memory (graph-safe);
+// tensor_id: 0 duration noise, 1 silence noise, 2 latent noise (see include/flamed_b200.h for the exact map)
+void launch_philox_normal(const uint64_t* seed_dev, uint32_t tensor_id, float scale, const float* add, int64_t n,
+                          float* out, cudaStream_t s);
 void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
 void launch_fill_random(void* x, int is_bf16, int64_t n, uint32_t seed, float scale, cudaStream_t stream);
 
@@ -124,6 +128,10 @@ void launch_lr_plan(const float* phone, const float* sil, const int64_t* src_len
                     int64_t* tgt_len, cudaStream_t stream);
 void launch_lr_expand(const float* x, const int32_t* cumsum, int B, int P, int H, int Tmax, float* out,
                       int32_t* out_index, cudaStream_t stream);
+
+// expand into a batch whose samples come from different earlier batches: per-sample source rows / cumsum / P
+void launch_lr_expand_gather(const float* const* xs, const int32_t* const* css, const int32_t* Ps, int B, int H,
+                             int Tmax, float* out, int32_t* out_index, cudaStream_t stream);
 
 // ---- codec
 struct Act1d {

@@ -51,6 +51,54 @@ __global__ void noise_init_kernel(const float* noise, const float* cond, float t
   if (i < n) x[i] = __fadd_rn(__fmul_rn(noise[i], temperature), cond[i]);
 }
 
+// ---- counter-based noise (Philox4x32-10 + Box-Muller).  Documented seed -> tensor map (include/flamed_b200.h):
+//   group g = i >> 2 of flat element index i;  (r0,r1,r2,r3) = Philox4x32-10(counter = (g_lo, g_hi, tensor_id, 0),
+//   key = (seed_lo, seed_hi));  u_k = ((r_k >> 8) + 0.5) * 2^-24 in (0,1);
+//   z0 = sqrt(-2 ln u0) cos(2 pi u1), z1 = sqrt(-2 ln u0) sin(2 pi u1), z2 / z3 the same from (u2, u3);  noise[i] = z[i & 3]
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&r)[4]) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t group, uint32_t tensor_id, float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)group, (uint32_t)(group >> 32), tensor_id, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float u[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) u[k] = ((float)(r[k] >> 8) + 0.5f) * 5.9604644775390625e-08f;  // exact in fp32
+#pragma unroll
+  for (int k = 0; k < 4; k += 2) {
+    const float rad = sqrtf(-2.0f * logf(u[k]));
+    float sn, cs;
+    sincospif(2.0f * u[k + 1], &sn, &cs);
+    z[k] = rad * cs;
+    z[k + 1] = rad * sn;
+  }
+}
+// out[i] = z[i] * scale (+ add[i]); thread = one group of 4 consecutive elements
+__global__ void philox_normal_kernel(const uint64_t* seed, uint32_t tensor_id, float scale, const float* add, int64_t n,
+                                     float* out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 4 >= n) return;
+  float z[4];
+  philox_normal4(*seed, (uint64_t)g, tensor_id, z);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = g * 4 + k;
+    if (i < n) {
+      const float v = __fmul_rn(z[k], scale);
+      out[i] = add ? __fadd_rn(v, add[i]) : v;
+    }
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* x, bf16* y, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = __float2bfloat16_rn(x[i]);
@@ -208,6 +256,37 @@ __global__ void __launch_bounds__(256) lr_expand_kernel(const float* x, const in
   if (out_index && lane == 0) out_index[(int64_t)b * Tmax + f] = src;
 }
 
+// same expand for a batch gathered from several earlier batches: sample b reads its own source rows xs[b] (P[b], H)
+// and its own inclusive cumsum cs[b] (2 P[b]); frames >= its total are zero padding
+__global__ void __launch_bounds__(256) lr_expand_gather_kernel(const float* const* xs, const int32_t* const* css,
+                                                               const int32_t* Ps, int H, int Tmax, float* out,
+                                                               int32_t* out_index) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (f >= Tmax) return;
+  const int P = Ps[b];
+  const int32_t* cs = css[b];
+  const int32_t total = cs[2 * P - 1];
+  int src = -1;
+  if (f < total) {
+    int lo = 0, hi = 2 * P;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cs[mid] > f) hi = mid; else lo = mid + 1;
+    }
+    src = (lo & 1) ? 0 : (lo >> 1);
+  }
+  float* o = out + ((int64_t)b * Tmax + f) * H;
+  if (src >= 0) {
+    const float* s = xs[b] + (int64_t)src * H;
+    for (int c = lane; c < H; c += 32) o[c] = s[c];
+  } else {
+    for (int c = lane; c < H; c += 32) o[c] = 0.f;
+  }
+  if (out_index && lane == 0) out_index[(int64_t)b * Tmax + f] = src;
+}
+
 // deterministic pseudo-random fill in [-scale, scale] (benchmark operands; zeros would under-state power)
 template <typename T>
 __global__ void fill_random_kernel(T* x, int64_t n, uint32_t seed, float scale) {
@@ -253,6 +332,12 @@ void launch_silu_sum(const float* temb, const float* cvec, int nfe, int B, int C
 void launch_noise_init(const float* noise, const float* cond, float temperature, int64_t n, float* x, cudaStream_t s) {
   if (n == 0) return;
   noise_init_kernel<<<nblk(n), 256, 0, s>>>(noise, cond, temperature, n, x);
+  FLM_LAUNCH_CHECK();
+}
+void launch_philox_normal(const uint64_t* seed_dev, uint32_t tensor_id, float scale, const float* add, int64_t n,
+                          float* out, cudaStream_t s) {
+  if (n == 0) return;
+  philox_normal_kernel<<<nblk((n + 3) / 4), 256, 0, s>>>(seed_dev, tensor_id, scale, add, n, out);
   FLM_LAUNCH_CHECK();
 }
 void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
@@ -307,6 +392,14 @@ void launch_lr_expand(const float* x, const int32_t* cumsum, int B, int P, int H
   if (B == 0 || Tmax == 0) return;
   dim3 grid((Tmax + 7) / 8, B);
   lr_expand_kernel<<<grid, 256, 0, stream>>>(x, cumsum, P, H, Tmax, out, out_index);
+  FLM_LAUNCH_CHECK();
+}
+
+void launch_lr_expand_gather(const float* const* xs, const int32_t* const* css, const int32_t* Ps, int B, int H,
+                             int Tmax, float* out, int32_t* out_index, cudaStream_t stream) {
+  if (B == 0 || Tmax == 0) return;
+  dim3 grid((Tmax + 7) / 8, B);
+  lr_expand_gather_kernel<<<grid, 256, 0, stream>>>(xs, css, Ps, H, Tmax, out, out_index);
   FLM_LAUNCH_CHECK();
 }
 

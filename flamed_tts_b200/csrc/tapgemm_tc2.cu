@@ -558,11 +558,7 @@ void launch_one(const TapGemm& p, const CUtensorMap* tm, Sched2 sch, int num_sms
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   sch.stages = stages;
   const int smem = 1024 + stages * stage_bytes<BLOCK_N>() + epi_bytes + BAR_BYTES;
-  static int configured = 0;  // per instantiation: opt in to the full dynamic shared memory once
-  if (configured < smem) {
-    FLM_CUDA(cudaFuncSetAttribute(tapgemm_tc2_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured = SMEM_LIMIT;
-  }
+  // the dynamic shared-memory opt-in of every instantiation is done per device in tapgemm_tc2_init (flm_ctx_create)
   const int pairs = sch.num_tiles < num_sms / 2 ? sch.num_tiles : num_sms / 2;
   tapgemm_tc2_kernel<BLOCK_N, EPI><<<2 * pairs, NUM_THREADS, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p, sch);
   FLM_LAUNCH_CHECK();

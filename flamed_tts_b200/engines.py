@@ -105,11 +105,14 @@ class DurationEngine:
             self.lib.flm_durgen_destroy(self.handle)
             self.handle = None
 
-    def sample(self, enc, src_mask, noise_dur, noise_sil, ts, temperature):
+    def sample(self, enc, src_mask, noise_dur, noise_sil, ts, temperature, seed=0):
+        """noise_dur / noise_sil: (B,P) standard-normal draws, or both None: drawn inside the library from `seed`
+        (documented Philox map, include/flamed_b200.h)"""
         dev = self.ctx.device
         enc = _f32(enc, dev)
         B, P, _ = enc.shape
-        noise_dur, noise_sil = _f32(noise_dur, dev), _f32(noise_sil, dev)
+        if noise_dur is not None:
+            noise_dur, noise_sil = _f32(noise_dur, dev), _f32(noise_sil, dev)
         mask = src_mask.to(device=dev, dtype=torch.uint8).contiguous()
         ts = ts.detach().to(device="cpu", dtype=torch.float32).contiguous()
         nfe = ts.numel() - 1
@@ -117,23 +120,40 @@ class DurationEngine:
         sil = torch.empty_like(phone)
         dur_t = torch.empty_like(phone)
         sil_t = torch.empty_like(phone)
-        check(self.lib.flm_durgen_sample(self.handle, _ptr(enc), _ptr(noise_dur), _ptr(noise_sil), _ptr(mask),
+        check(self.lib.flm_durgen_sample(self.handle, _ptr(enc), _ptr(noise_dur), _ptr(noise_sil), int(seed), _ptr(mask),
                                          c_void_p(ts.data_ptr()), nfe, float(temperature), B, P, _ptr(phone),
                                          _ptr(sil), _ptr(dur_t), _ptr(sil_t), self.ctx.stream()))
         return phone, sil, dur_t, sil_t
 
-    def length_regulate(self, x, phone_dur, sil_dur, src_lens, return_index=False):
+    def forward(self, which, x, enc, t, src_mask=None):
+        """one ProbabilisticModule.forward evaluation (pva.py:221-238): which 0 = duration, 1 = silence generator"""
         dev = self.ctx.device
-        x = _f32(x, dev)
-        B, P, H = x.shape
+        x, enc = _f32(x, dev), _f32(enc, dev)
+        B, P, _ = enc.shape
+        mask = src_mask.to(device=dev, dtype=torch.uint8).contiguous() if src_mask is not None else None
+        out = torch.empty((B, P), device=dev, dtype=torch.float32)
+        check(self.lib.flm_durgen_forward(self.handle, int(which), _ptr(x), _ptr(enc), float(t), _ptr(mask), B, P,
+                                          _ptr(out), self.ctx.stream()))
+        return out
+
+    def plan(self, phone_dur, sil_dur, src_lens, sync=True):
+        """integer plan of the length regulator -> (cumsum (B,2P) i32, tgt_len (B,) i64 on device, Tmax or None)"""
+        dev = self.ctx.device
         phone_dur, sil_dur = _f32(phone_dur, dev), _f32(sil_dur, dev)
+        B, P = phone_dur.shape
         src_lens = src_lens.to(device=dev, dtype=torch.int64).contiguous()
         cumsum = torch.empty((B, 2 * P), device=dev, dtype=torch.int32)
         tgt_len = torch.empty((B,), device=dev, dtype=torch.int64)
         tmax = c_int64(0)
         check(self.lib.flm_lr_plan(self.ctx.handle, _ptr(phone_dur), _ptr(sil_dur), _ptr(src_lens), B, P,
-                                   _ptr(cumsum), _ptr(tgt_len), byref(tmax), self.ctx.stream()))
-        T = int(tmax.value)
+                                   _ptr(cumsum), _ptr(tgt_len), byref(tmax) if sync else None, self.ctx.stream()))
+        return cumsum, tgt_len, (int(tmax.value) if sync else None)
+
+    def length_regulate(self, x, phone_dur, sil_dur, src_lens, return_index=False):
+        dev = self.ctx.device
+        x = _f32(x, dev)
+        B, P, H = x.shape
+        cumsum, tgt_len, T = self.plan(phone_dur, sil_dur, src_lens, sync=True)
         out = torch.empty((B, T, H), device=dev, dtype=torch.float32)
         index = torch.empty((B, T), device=dev, dtype=torch.int32) if return_index else None
         check(self.lib.flm_lr_expand(self.ctx.handle, _ptr(x), _ptr(cumsum), B, P, H, T, _ptr(out), _ptr(index),
@@ -141,6 +161,20 @@ class DurationEngine:
         if return_index:
             return out, tgt_len, index
         return out, tgt_len
+
+    def expand_gather(self, sources, Tmax):
+        """sources: list over the B samples of the new batch of (x (Pmax,H) f32 row block of that sample, cumsum (2 Pmax)
+        i32 of that sample), both views into tensors of earlier planned batches -> (B,Tmax,H) f32, zero-padded"""
+        dev = self.ctx.device
+        B = len(sources)
+        H = sources[0][0].shape[-1]
+        table = torch.tensor([[x.data_ptr() for x, _ in sources], [c.data_ptr() for _, c in sources]], dtype=torch.int64)
+        ps = torch.tensor([x.shape[0] for x, _ in sources], dtype=torch.int32)
+        table, ps = table.to(dev, non_blocking=True), ps.to(dev, non_blocking=True)
+        out = torch.empty((B, Tmax, H), device=dev, dtype=torch.float32)
+        check(self.lib.flm_lr_expand_gather(self.ctx.handle, _ptr(table[0]), _ptr(table[1]), _ptr(ps), B, H, int(Tmax),
+                                            _ptr(out), None, self.ctx.stream()))
+        return out
 
 
 class DenoiserEngine:
@@ -181,17 +215,19 @@ class DenoiserEngine:
         check(self.lib.flm_cond_prepare(self.handle, _ptr(prior_embs), _ptr(mask), B, L, _ptr(out), self.ctx.stream()))
         return out
 
-    def sample(self, cond, spk, noise, ts, temperature, use_graph=True):
-        """returns latents channels-last (B,L,D); the reference's (B,D,L) is `.transpose(1,2)` of it"""
+    def sample(self, cond, spk, noise, ts, temperature, use_graph=True, seed=0):
+        """returns latents channels-last (B,L,D); the reference's (B,D,L) is `.transpose(1,2)` of it.
+        noise None: x0 = temperature * N(0,1) + cond is drawn inside the init kernel from `seed` (Philox map)"""
         dev = self.ctx.device
-        cond, spk, noise = _f32(cond, dev), _f32(spk, dev), _f32(noise, dev)
+        cond, spk = _f32(cond, dev), _f32(spk, dev)
+        noise = _f32(noise, dev) if noise is not None else None
         B, L, D = cond.shape
         ts = ts.detach().to(device="cpu", dtype=torch.float32).contiguous()
         nfe = ts.numel() - 1
         out = torch.empty((B, L, D), device=dev, dtype=torch.float32)
-        check(self.lib.flm_denoiser_sample(self.handle, _ptr(cond), _ptr(spk), _ptr(noise), c_void_p(ts.data_ptr()), B,
-                                           L, nfe, float(temperature), _ptr(out), 1 if use_graph else 0,
-                                           self.ctx.stream()))
+        check(self.lib.flm_denoiser_sample(self.handle, _ptr(cond), _ptr(spk), _ptr(noise), int(seed),
+                                           c_void_p(ts.data_ptr()), B, L, nfe, float(temperature), _ptr(out),
+                                           1 if use_graph else 0, self.ctx.stream()))
         return out
 
     def forward(self, x, t, spk):
@@ -264,6 +300,22 @@ class CodecEncoderEngine:
         out = torch.empty((B, 256, T), device=dev, dtype=torch.float32)
         check(self.lib.flm_codec_encode(self.handle, _ptr(wav), B, S, _ptr(out), self.ctx.stream()))
         return out
+
+
+def wav_to_pcm16(ctx, wav):
+    """fp32 waveform tensor (any shape, contiguous) -> int16 PCM of the same shape on the device: lrintf(x * 32767),
+    what soundfile stores for the reference's sf.write(path, wav, 16000) (synthesize.py:296)"""
+    wav = _f32(wav, ctx.device)
+    out = torch.empty(wav.shape, device=ctx.device, dtype=torch.int16)
+    check(ctx.lib.flm_wav_to_pcm16(ctx.handle, _ptr(wav), wav.numel(), _ptr(out), ctx.stream()))
+    return out
+
+
+def philox_normal(ctx, seed, tensor_id, n):
+    """the library's documented seed -> N(0,1) map (tests)"""
+    out = torch.empty((n,), device=ctx.device, dtype=torch.float32)
+    check(ctx.lib.flm_philox_normal(ctx.handle, int(seed), int(tensor_id), int(n), _ptr(out), ctx.stream()))
+    return out
 
 
 def tapgemm(ctx, precision, A, W, bias, T_out, ntaps, off0, dil, stride, epi):

@@ -20,8 +20,10 @@
  *     `stream` and never synchronise, except flm_lr_plan (one documented sync; the
  *     reference syncs at the same place, pva.py:158).
  *   - activations are channels-last: (B, T, C) with C contiguous.
- *   - a handle is not thread-safe; one handle per (device, stream).  Workspaces and
- *     CUDA-graph caches belong to the handle, keyed by (B, L, nfe).
+ *   - a handle is NOT thread-safe and is bound to one stream at a time: its workspaces and CUDA-graph
+ *     cache (keyed by (B, L, nfe), bounded, LRU) are reused by every call, so two calls on the same
+ *     handle must be ordered on one stream (or by events).  Different handles may be driven from
+ *     different threads / streams.  Every entry point restores the caller's current CUDA device.
  *   - there is no CPU fallback: every entry point fails with FLM_ERR_CUDA if no
  *     sm_100 device is present.
  */
@@ -49,6 +51,7 @@ typedef struct flm_durgen flm_durgen;
 typedef struct flm_denoiser flm_denoiser;
 typedef struct flm_codec_dec flm_codec_dec;
 typedef struct flm_codec_enc flm_codec_enc;
+typedef struct flm_comm flm_comm;
 typedef void* flm_stream; /* cudaStream_t */
 
 typedef struct {
@@ -73,24 +76,48 @@ void flm_ctx_destroy(flm_ctx* ctx);
  * Always fp32 FMA (durations must round identically to the reference). */
 int flm_durgen_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_durgen** out);
 void flm_durgen_destroy(flm_durgen* h);
-/* enc (B,P,192) f32; noise_* (B,P) f32 standard normal (dur first, pva.py:101-102);
+/* enc (B,P,192) f32; noise_* (B,P) f32 standard normal (dur first, pva.py:101-102), or BOTH NULL: the two draws are
+ * then made inside the library from `seed` with the documented counter-based map below (tensor ids 0 and 1);
  * src_mask (B,P) u8, 1 = padding; ts (nfe+1) f32 HOST = torch.linspace(0,1,nfe+1);
  * out_phone/out_sil (B,P) f32 holding clamp(round(exp(x)-1),0); out_dur_t/out_sil_t (B,P) f32
- * = the ODE state before rounding (may be NULL). */
-int flm_durgen_sample(flm_durgen* h, const float* enc, const float* noise_dur, const float* noise_sil,
+ * = the ODE state before rounding (may be NULL).
+ *
+ * Seed -> tensor map (flm_philox_normal returns exactly these values): for flat element index i of a tensor,
+ *   g = i >> 2;  (r0,r1,r2,r3) = Philox4x32-10(counter = (g & 0xffffffff, g >> 32, tensor_id, 0),
+ *                                              key = (seed & 0xffffffff, seed >> 32));
+ *   u_k = ((r_k >> 8) + 0.5) * 2^-24;  z0 = sqrt(-2 ln u0) cos(2 pi u1), z1 = sqrt(-2 ln u0) sin(2 pi u1),
+ *   z2, z3 likewise from (u2, u3);  noise[i] = z[i & 3].
+ * tensor_id: 0 = duration noise (B,P), 1 = silence noise (B,P), 2 = latent noise (B,L,D). */
+int flm_durgen_sample(flm_durgen* h, const float* enc, const float* noise_dur, const float* noise_sil, uint64_t seed,
                       const uint8_t* src_mask, const float* ts_host, int nfe, float temperature, int B, int P,
                       float* out_phone, float* out_sil, float* out_dur_t, float* out_sil_t, flm_stream stream);
+/* replaces: ProbabilisticModule.forward, pva.py:221-238 - one vector-field evaluation of generator `which`
+ * (0 = duration_generator, 1 = sil_generator): x (B,P) f32, enc (B,P,192) f32, scalar t, src_mask (B,P) u8 1 = padding
+ * (nullable) -> out_v (B,P) f32 (masked positions 0). */
+int flm_durgen_forward(flm_durgen* h, int which, const float* x, const float* enc, float t, const uint8_t* src_mask,
+                       int B, int P, float* out_v, flm_stream stream);
+/* n values of the map above (tests / documentation of the map) */
+int flm_philox_normal(flm_ctx* ctx, uint64_t seed, int tensor_id, int64_t n, float* out, flm_stream stream);
 
 /* ---------------------------------------------------------------- length regulator
  * replaces: LengthRegulator.LR, pva.py:125-166 (+ pad, flamed/utils/tools.py:299-317).
  * plan: integer repeats -> inclusive cumsum (B,2P) i32 + tgt_len (B) i64 on device, and the
- * batch maximum on the host (one stream sync, as pva.py:158 `.tolist()`). */
+ * batch maximum on the host (one stream sync, as pva.py:158 `.tolist()`).  out_tmax_host == NULL: no
+ * synchronisation, the caller reads tgt_len itself later (metadata path: every front batch is planned first,
+ * one sync for all of them, then the utterances are re-bucketed by their real frame counts). */
 int flm_lr_plan(flm_ctx* ctx, const float* phone_dur, const float* sil_dur, const int64_t* src_lens, int B, int P,
                 int32_t* out_cumsum, int64_t* out_tgt_len, int64_t* out_tmax_host, flm_stream stream);
 /* expand: out (B,Tmax,H) f32 = gather of x (B,P,H) f32, zero beyond tgt_len;
  * out_index (B,Tmax) i32 = source phoneme row, -1 for padding (may be NULL). */
 int flm_lr_expand(flm_ctx* ctx, const float* x, const int32_t* cumsum, int B, int P, int H, int Tmax, float* out,
                   int32_t* out_index, flm_stream stream);
+
+/* the same expand for a batch whose B samples come from different planned batches: x_rows[b] -> (P[b],H) f32 rows,
+ * cumsums[b] -> (2 P[b]) i32 of sample b (device arrays of device pointers); frames >= the sample's total are zero
+ * (the re-padding of tools.py:299-317 to the new batch maximum Tmax). */
+int flm_lr_expand_gather(flm_ctx* ctx, const float* const* x_rows, const int32_t* const* cumsums,
+                         const int32_t* P_per_sample, int B, int H, int Tmax, float* out, int32_t* out_index,
+                         flm_stream stream);
 
 /* ---------------------------------------------------------------- code-decoder denoiser
  * replaces: ProbGenerator.sample, flamed/models/synthesizer/prob_generator.py:434-446
@@ -105,13 +132,15 @@ void flm_denoiser_destroy(flm_denoiser* h);
 /* prior_embs (B,Q,L,cond_dim) f32; mask (B,L) u8, 1 = valid frame; out_cond (B,L,target_dim) f32 */
 int flm_cond_prepare(flm_denoiser* h, const float* prior_embs, const uint8_t* mask, int B, int L, float* out_cond,
                      flm_stream stream);
-/* cond (B,L,D) f32; spk (B,spk_dim) f32; noise (B,L,D) f32 standard normal (prob_generator.py:440);
+/* cond (B,L,D) f32; spk (B,spk_dim) f32; noise (B,L,D) f32 standard normal (prob_generator.py:440) or NULL: the
+ * draw is then fused into the x0 = temperature * noise + cond kernel from `seed` (tensor id 2 of the map above);
  * ts (nfe+1) f32 HOST; out_latents (B,L,D) f32 channels-last: the reference returns its
- * transpose(1,2) VIEW (prob_generator.py:446).  The whole nfe-step loop runs as one CUDA graph
- * (use_graph != 0), cached per (B,L,nfe). */
-int flm_denoiser_sample(flm_denoiser* h, const float* cond, const float* spk, const float* noise, const float* ts_host,
-                        int B, int L, int nfe, float temperature, float* out_latents, int use_graph,
-                        flm_stream stream);
+ * transpose(1,2) VIEW (prob_generator.py:446).  use_graph != 0: the whole nfe-step loop runs as one CUDA graph;
+ * a (B,L,nfe) key is launched directly the first time it is seen, captured when it comes back, and at most 8
+ * executables are kept per handle (least recently used first out). */
+int flm_denoiser_sample(flm_denoiser* h, const float* cond, const float* spk, const float* noise, uint64_t seed,
+                        const float* ts_host, int B, int L, int nfe, float temperature, float* out_latents,
+                        int use_graph, flm_stream stream);
 /* one velocity evaluation v = denoiser(x, t, spk) (SimpleMLPAdaLN.forward), for parity tests */
 int flm_denoiser_forward(flm_denoiser* h, const float* x, const float* spk, float t, int B, int L, float* out_v,
                          flm_stream stream);
@@ -140,6 +169,23 @@ void flm_codec_enc_destroy(flm_codec_enc* h);
 int64_t flm_codec_enc_frames(flm_codec_enc* h, int64_t S);
 /* wav (B,1,S) f32; out (B,256,T') f32 in the REFERENCE layout (channels-first) */
 int flm_codec_encode(flm_codec_enc* h, const float* wav, int B, int64_t S, float* out, flm_stream stream);
+
+/* ---------------------------------------------------------------- waveform write-out and the final gather
+ * replaces: the per-item `wav_tensor[0].detach().cpu().numpy()` + `sf.write(path, wav, 16000)` of
+ *           /root/reference/synthesize.py:293-298 (soundfile stores PCM_16: lrintf(x * 32767)).
+ * flm_wav_to_pcm16: n fp32 samples -> n int16 samples on the device, so that half the bytes cross PCIe / NVLink. */
+int flm_wav_to_pcm16(flm_ctx* ctx, const float* wav, int64_t n, int16_t* out, flm_stream stream);
+/* The path's only collective (one process per GPU, utterances sharded, no exchange inside the loops): gather of the
+ * PCM waveforms to `root` over NCCL send/recv (NVLink).  flm_comm_unique_id fills 128 bytes (ncclUniqueId) on one rank;
+ * the caller ships them to every rank (torch.distributed broadcast) and each rank calls flm_comm_create.
+ * flm_gather_wav: rank r contributes counts[r] int16 samples (counts: HOST array, world entries, same on all ranks;
+ * counts[rank] == n_send); on the root they land back to back in rank order in `recv` (>= sum(counts) samples; NULL
+ * elsewhere).  Enqueues on `stream`, never synchronises. */
+int flm_comm_unique_id(unsigned char* out128);
+int flm_comm_create(flm_ctx* ctx, const unsigned char* id128, int world, int rank, flm_comm** out);
+void flm_comm_destroy(flm_comm* c);
+int flm_gather_wav(flm_comm* c, const int16_t* send, int64_t n_send, int16_t* recv, const int64_t* counts, int root,
+                   flm_stream stream);
 
 /* ---------------------------------------------------------------- per-launch profiler (bench.py roofline)
  * While enabled, every kernel launch made outside a CUDA-graph capture is bracketed by CUDA events on

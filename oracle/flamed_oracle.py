@@ -406,22 +406,45 @@ def codec_prompt_features(sd, enc_out, n_q=(1, 2, 3)):
 # ----------------------------------------------------------------------------- whole path
 
 
-def sample_batch(sd, cfg, phonemes, src_lens, prompts, timbres, noise_dur, noise_sil, noise_lat_fn,
-                 nfe_dur, nfe_den, temp_dur, temp_den, codec_sd=None):
-    """Flamed.sample_batch, flamed.py:168-217, with the three CPU randn draws
-    (pva.py:101-102, prob_generator.py:440) injected.  `noise_lat_fn(B, L)` returns
-    the (B,L,256) draw once L is known."""
+def front_stage(sd, cfg, phonemes, src_lens, noise_dur, noise_sil, nfe_dur, temp_dur):
+    """first half of Flamed.sample_batch (flamed.py:183-196 -> prior_generator.py:141-161): phoneme encoder, the two
+    duration ODEs + rounding, length regulator.  Returns a dict with x (B,Tmax,192) zero-padded and tgt_len."""
     P = "prior_generator"
     src_mask = get_mask_from_lengths(src_lens, phonemes.shape[1])
     enc = phoneme_encoder(sd, P + ".encoder", phonemes, src_mask, cfg["prior_generator"]["transformer"]["encoder_head"])
     phone, sil, dur_t, sil_t = durgen_sample(sd, P + ".pva", enc, src_mask, noise_dur, noise_sil, nfe_dur, temp_dur)
     x, tgt_len = length_regulator(enc, phone, sil, src_lens)
-    prior_embs, logits, tgt_mask = prior_after_pva(sd, P, x, tgt_len, prompts, cfg["prior_generator"])
+    return dict(enc=enc, phone_dur=phone, sil_dur=sil, dur_t=dur_t, sil_t=sil_t, x=x, tgt_len=tgt_len)
+
+
+def back_stage(sd, cfg, x, tgt_len, prompts, timbres, noise_lat_fn, nfe_den, temp_den, codec_sd=None):
+    """second half of Flamed.sample_batch (prior_generator.py:162-181, flamed.py:198-215) on a length-regulated,
+    zero-padded batch x (B,Tmax,192): prior decoders, cond fold, denoiser loop, codec."""
+    prior_embs, logits, tgt_mask = prior_after_pva(sd, "prior_generator", x, tgt_len, prompts, cfg["prior_generator"])
     cond = cond_prepare(sd, "prob_generator", prior_embs, ~tgt_mask.unsqueeze(-1))
     noise = noise_lat_fn(cond.shape[0], cond.shape[1])
     latents = denoiser_sample(sd, "prob_generator", cond, timbres, noise, nfe_den, temp_den)
-    out = dict(enc=enc, phone_dur=phone, sil_dur=sil, dur_t=dur_t, sil_t=sil_t, tgt_len=tgt_len,
-               prior_embs=prior_embs, prior_logits=logits, tgt_mask=tgt_mask, cond=cond, latents=latents)
+    out = dict(prior_embs=prior_embs, prior_logits=logits, tgt_mask=tgt_mask, cond=cond, latents=latents)
     if codec_sd is not None:
         out["wav"] = codec_decode(codec_sd, latents, timbres)
+    return out
+
+
+def repad(xs, tgt_lens):
+    """utterances (each (Tmax_i,192) from its own front batch, with its frame count) -> one zero-padded batch: what
+    tools.py:299-317 `pad` does inside the length regulator, applied to a different grouping of the same utterances"""
+    T = int(max(tgt_lens))
+    out = torch.zeros((len(xs), T, xs[0].shape[-1]), dtype=xs[0].dtype)
+    for i, (x, n) in enumerate(zip(xs, tgt_lens)):
+        out[i, : int(n)] = x[: int(n)]
+    return out
+
+
+def sample_batch(sd, cfg, phonemes, src_lens, prompts, timbres, noise_dur, noise_sil, noise_lat_fn,
+                 nfe_dur, nfe_den, temp_dur, temp_den, codec_sd=None):
+    """Flamed.sample_batch, flamed.py:168-217, with the three CPU randn draws
+    (pva.py:101-102, prob_generator.py:440) injected.  `noise_lat_fn(B, L)` returns
+    the (B,L,256) draw once L is known."""
+    out = front_stage(sd, cfg, phonemes, src_lens, noise_dur, noise_sil, nfe_dur, temp_dur)
+    out.update(back_stage(sd, cfg, out["x"], out["tgt_len"], prompts, timbres, noise_lat_fn, nfe_den, temp_den, codec_sd))
     return out

@@ -1,18 +1,20 @@
-"""Import the UNMODIFIED reference (/root/reference) in the build container.
+"""Import the UNMODIFIED reference: /root/reference in the build container, or its verbatim git-ignored copy
+`oracle/_ref/` (made by oracle/make_ref.py, travels to the GPU box with the gpurun snapshot).
 
-TEST INFRASTRUCTURE ONLY.  The reference is pure Python/PyTorch but imports a
+TEST / BENCH INFRASTRUCTURE ONLY.  The reference is pure Python/PyTorch but imports a
 dozen packages that are absent here (librosa, lightning, g2p_en, ...); none of
 them is touched by the inference hot path, so they are replaced by empty stub
-modules before `import flamed` (recipe: SURVEY.md Appendix B).  This module is
-used only by `oracle/make_golden.py` and by tests that pin the oracle port
-against the live reference; `/root/reference` does not exist on the GPU box, so
-nothing under `-m gpu`, `smoke()` or `bench.py` may import this file.
+modules before `import flamed` (recipe: SURVEY.md Appendix B).  Users: `oracle/make_golden.py`,
+tests that pin the oracle port against the live reference, and bench.py's `--impl reference` (CPU) and
+`--impl eager` (the reference's own PyTorch code on the same B200) arms.  Never a product path.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FLAMED_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_ROOT = os.environ.get("FLAMED_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/flamed") else os.path.join(_HERE, "_ref"))
 
 
 def reference_available() -> bool:
@@ -78,3 +80,33 @@ def import_reference():
         for k in list(mods):
             del sys.modules[k]
     return mods
+
+
+def build_reference_models(flamed_sd, codec_dec_sd=None, codec_enc_sd=None, device="cpu"):
+    """The reference's own modules with the given (seeded) weights loaded: (cfg, Flamed, FACodecEncoder|None,
+    FACodecDecoder|None), in eval mode on `device`.  Construction arguments of the codec: synthesize.py:46-69."""
+    import torch
+    import yaml
+    mods = import_reference()
+    with open(os.path.join(REFERENCE_ROOT, "configs", "prior.yaml")) as f:
+        prior = yaml.safe_load(f)
+    with open(os.path.join(REFERENCE_ROOT, "configs", "prob.yaml")) as f:
+        prob = yaml.safe_load(f)
+    cfg = {"prior_generator": prior, "prob_generator": prob}
+    model = mods["flamed.models.flamed"].Flamed(cfg).eval()
+    model.load_state_dict(flamed_sd, strict=True)
+    fm = mods["flamed.models.facodec.facodec"]
+    enc = dec = None
+    if codec_enc_sd is not None:
+        enc = fm.FACodecEncoder(ngf=32, up_ratios=[2, 4, 5, 5], out_channels=256).eval()
+        enc.load_state_dict(codec_enc_sd, strict=True)
+        enc = enc.to(device)
+    if codec_dec_sd is not None:
+        dec = fm.FACodecDecoder(in_channels=256, upsample_initial_channel=1024, ngf=32, up_ratios=[5, 5, 4, 2],
+                                vq_num_q_c=2, vq_num_q_p=1, vq_num_q_r=3, vq_dim=256, codebook_dim=8,
+                                codebook_size_prosody=10, codebook_size_content=10, codebook_size_residual=10,
+                                use_gr_x_timbre=True, use_gr_residual_f0=True, use_gr_residual_phone=True).eval()
+        res = dec.load_state_dict(codec_dec_sd, strict=False)  # training-only heads keep their own init
+        assert not res.unexpected_keys, res.unexpected_keys
+        dec = dec.to(device)
+    return cfg, model.to(device), enc, dec

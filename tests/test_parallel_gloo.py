@@ -28,6 +28,37 @@ def test_bucketing_and_dealing_cover_every_utterance_once():
     assert P.deal_buckets(lengths, buckets, 2) == P.deal_buckets(lengths, buckets, 2)  # deterministic
 
 
+def test_row_budget_bucketing():
+    rng = torch.Generator().manual_seed(0)
+    lens = torch.randint(150, 1300, (500,), generator=rng).tolist()
+    for budget, maxb in ((16384, 64), (32768, 64), (65536, 128), (10 ** 9, 64)):
+        buckets = P.bucket_by_rows(lens, budget, maxb)
+        assert sorted(i for b in buckets for i in b) == list(range(500))
+        for b in buckets:
+            longest = max(lens[i] for i in b)
+            assert len(b) <= maxb and (len(b) == 1 or len(b) * longest <= budget)
+            assert lens[b[0]] == longest  # sorted inside: the first member is the padded length
+        for a, b in zip(buckets, buckets[1:]):
+            assert min(lens[i] for i in a) >= max(lens[i] for i in b)
+    # padding overhead of exact-length bucketing stays small
+    buckets = P.bucket_by_rows(lens, 32768, 64)
+    padded = sum(len(b) * max(lens[i] for i in b) for b in buckets)
+    assert padded / sum(lens) < 1.10
+    assert P.bucket_by_rows([], 100, 4) == [] and P.bucket_by_rows([5000], 100, 4) == [[0]]
+
+
+def test_shard_of_a_global_pool_is_a_partition():
+    """bench.py / synthesize.py: every rank derives its share from the same seeded pool with no communication"""
+    for world in (2, 4, 8):
+        wl = W.metadata_workload(256 * world, 64, seed=0)  # bench.py's default pool: 256 utterances per GPU
+        lens = [p.numel() for p in wl["phonemes"]]
+        buckets = P.bucket_by_length(lens, 64)
+        shares = [P.deal_buckets(lens, buckets, world)[r] for r in range(world)]
+        assert sorted(i for sh in shares for b in sh for i in b) == list(range(256 * world))
+        cost = [sum(P.bucket_cost(lens, b) for b in sh) for sh in shares]
+        assert max(cost) / (sum(cost) / world) < 1.03  # greedy LPT keeps the straggler within 3 % of the mean
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -42,9 +73,14 @@ def _worker(rank, world, port, q):
                 gr = torch.Generator().manual_seed(100 + r)
                 ref = [torch.randn(2 + r, 1, 400 * (k + 1 + r), generator=gr) for k in range(2 + r)]
                 ok = ok and len(out[r]) == len(ref) and all(torch.equal(a, b) for a, b in zip(out[r], ref))
-            q.put(ok)
         else:
             assert out is None
+        # int16 PCM (what the GPU path ships), one rank with nothing to send
+        pcm = [] if rank == 1 else [torch.arange(-5, 7, dtype=torch.int16).view(2, 1, 6)]
+        out = P.gather_waveforms(pcm, rank, world)
+        if rank == 0:
+            ok = ok and out[1] == [] and out[0][0].dtype == torch.int16 and torch.equal(out[0][0], pcm[0])
+            q.put(ok)
     finally:
         dist.destroy_process_group()
 
