@@ -4,8 +4,9 @@ Same constructors, `from_pretrained`, `forward` / `inference` signatures and sta
 layout (`block.N...`, `model.N...weight_g/weight_v/bias`, `...act.alpha/beta`,
 `...upsample.filter`, `...downsample.lowpass.filter`, `quantizer.*`, `timbre_encoder.*`,
 `timbre_linear.*`) as the reference's flamed/models/facodec/facodec.py.  The convolution /
-anti-aliased Snake stacks run in sm_100a kernels (flm_codec_encode / flm_codec_decode); the
-prompt-side vector quantiser and timbre transformer are PyTorch glue.
+anti-aliased Snake stacks run in sm_100a kernels (flm_codec_encode / flm_codec_decode), and so
+do the prompt-side vector quantisers and the timbre transformer (flm_codec_dec_prompt, SURVEY.md
+section 8 f3); the nn.Modules below only hold the parameters in the reference's key layout.
 Training-only heads of the released decoder checkpoint (f0 / phone / x_timbre predictors) are
 accepted and ignored by `load_state_dict`.
 """
@@ -15,7 +16,6 @@ import os
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from flamed.models.synthesizer._engine import EngineOwner
 
@@ -118,7 +118,7 @@ class FACodecEncoder(EngineOwner):
 
 
 class _FVQ(nn.Module):
-    """factorised VQ layer (reference quantize/fvq.py:16-116), eval path"""
+    """parameters of one factorised VQ layer (reference quantize/fvq.py:16-116)"""
 
     def __init__(self, dim, codebook_size, codebook_dim):
         super().__init__()
@@ -126,32 +126,13 @@ class _FVQ(nn.Module):
         self.out_proj = _WN(dim, codebook_dim, 1, dim, linear=True)
         self._codebook = nn.Embedding(codebook_size, codebook_dim)
 
-    def forward(self, z):  # (B,D,T)
-        z_e = F.linear(z.transpose(1, 2), self.in_proj.weight(), self.in_proj.bias)
-        cb = self._codebook.weight
-        e, c = F.normalize(z_e.reshape(-1, z_e.shape[-1])), F.normalize(cb)
-        dist = e.pow(2).sum(1, keepdim=True) - 2 * e @ c.t() + c.pow(2).sum(1, keepdim=True).t()
-        idx = (-dist).max(1)[1].view(z.shape[0], -1)
-        z_q = z_e + (F.embedding(idx, cb) - z_e)
-        return F.linear(z_q, self.out_proj.weight(), self.out_proj.bias).transpose(1, 2), idx
-
 
 class _RVQ(nn.Module):
-    """residual VQ (reference quantize/rvq.py:14-73), eval path"""
+    """parameters of one residual VQ (reference quantize/rvq.py:14-73)"""
 
     def __init__(self, n, dim, codebook_size, codebook_dim):
         super().__init__()
         self.layers = nn.ModuleList(_FVQ(dim, 2 ** codebook_size, codebook_dim) for _ in range(n))
-
-    def forward(self, x):
-        residual, total, idxs, quants = x, 0.0, [], []
-        for layer in self.layers:
-            q, idx = layer(residual)
-            residual = residual - q
-            total = total + q
-            idxs.append(idx)
-            quants.append(q)
-        return total, torch.stack(idxs), torch.stack(quants)
 
 
 class _TimbreLayer(nn.Module):
@@ -163,15 +144,10 @@ class _TimbreLayer(nn.Module):
         self.ffn.ffn_1 = nn.Conv1d(d, filt, k, padding=k // 2)
         self.ffn.ffn_2 = nn.Linear(filt, d)
 
-    def forward(self, x):
-        h = self.ln_1(x)
-        x = x + self.self_attn(h, h, h, need_weights=False)[0]
-        h = F.relu(self.ffn.ffn_1(self.ln_2(x).transpose(1, 2)).transpose(1, 2))
-        return x + self.ffn.ffn_2(h)
-
 
 class _TimbreEncoder(nn.Module):
-    """reference facodec/transformer.py:154-234 (use_cln=False, no token embedding)"""
+    """parameters of the timbre transformer (reference facodec/transformer.py:154-234: use_cln=False, no token
+    embedding; the positional table is indexed by the batch axis, transformer.py:50-52)"""
 
     def __init__(self, d=256, n_layers=4):
         super().__init__()
@@ -183,12 +159,6 @@ class _TimbreEncoder(nn.Module):
         self.position_emb.register_buffer("pe", pe)
         self.layers = nn.ModuleList(_TimbreLayer(d) for _ in range(n_layers))
         self.last_ln = nn.LayerNorm(d)
-
-    def forward(self, x):  # (B,T,d)
-        x = x + self.position_emb.pe[: x.size(0)]  # indexed by the batch axis, as the reference does (transformer.py:50-52)
-        for layer in self.layers:
-            x = layer(x)
-        return self.last_ln(x)
 
 
 class FACodecDecoder(EngineOwner):
@@ -239,21 +209,17 @@ class FACodecDecoder(EngineOwner):
     def forward(self, x, vq=True, get_vq=False, eval_vq=True, speaker_embedding=None, n_quantizers=None,
                 quantized=None):
         """prompt side (vq=True): enc_out (B,256,T) -> (outs, codes (6,B,T) int64, commit, quantized_buf,
-        timbre (B,256)); reference facodec.py:509-533.  PyTorch glue, IEEE fp32."""
+        timbre (B,256)); reference facodec.py:509-533.  Runs in flm_codec_dec_prompt (fp32 kernels)."""
         if get_vq:
             return [layer._codebook.weight for q in self.quantizer for layer in q.layers]
         if not vq:
             raise NotImplementedError("FACodecDecoder.forward(vq=False) is a training path; use .inference()")
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            q0, i0, _ = self.quantizer[0](x)
-            q1, i1, _ = self.quantizer[1](x)
-            outs, qs, bufs = q0 + q1, [i0, i1], [q0, q1]
-            if self.vq_num_q_r > 0:
-                q2, i2, _ = self.quantizer[2](x - (q0 + q1))
-                outs, qs, bufs = outs + q2, qs + [i2], bufs + [q2]
-            spk = self.timbre_encoder(x.transpose(1, 2)).mean(dim=1)
-        codes = torch.cat(qs, dim=0)
-        return outs, codes, torch.zeros(codes.shape[0], x.shape[0], device=x.device), bufs, spk
+        codes, quant, spk = self.engine().prompt(x)
+        bufs = [quant[g] for g in range(len(self.quantizer))]
+        outs = bufs[0] + bufs[1]
+        if len(bufs) > 2:
+            outs = outs + bufs[2]
+        return outs, codes, torch.zeros(codes.shape[0], x.shape[0], device=codes.device), bufs, spk
 
     @torch.inference_mode()
     def inference(self, x, speaker_embedding):

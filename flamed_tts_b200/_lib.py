@@ -54,6 +54,7 @@ SIGNATURES = {
     "flm_codec_dec_destroy": (None, [c_void_p]),
     "flm_codec_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "flm_codec_dec_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "flm_codec_dec_prompt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "flm_codec_enc_load": (c_int, [c_void_p, POINTER(flm_tensor), c_int, POINTER(c_void_p)]),
     "flm_codec_enc_destroy": (None, [c_void_p]),
     "flm_codec_enc_frames": (c_int64, [c_void_p, c_int64]),

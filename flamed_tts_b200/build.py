@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflamed_b200.so")
-SOURCES = ["api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "dwconv_tc.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_codec.cu", "comm.cu"]
+SOURCES = ["api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "dwconv_tc.cu", "dwconv_fused.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_codec.cu", "comm.cu", "prompt_side.cu"]
 HEADERS = ["common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "flamed_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -52,10 +52,12 @@ def build(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
+        tmp = LIB + ".tmp%d" % os.getpid()
+        cmd = [_nvcc(), "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, LIB)  # atomic: a concurrent reader (or a snapshot of the tree) never sees a half-written library
     return LIB
 
 

@@ -53,6 +53,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
   tapgemm_tc_init();
   tapgemm_tc2_init();
   dwconv_tc_init();
+  dwconv_fused_init();
   if (const char* g = getenv("FLAMED_B200_GEMM")) c->gemm_gen = atoi(g) == 1 ? 1 : 2;
   kernels_norm_init();
   *out = c.release();
@@ -307,7 +308,7 @@ extern "C" int flm_lr_expand_gather(flm_ctx* ctx, const float* const* x_rows, co
 // ===================================================================================== denoiser
 namespace {
 struct ConvNeXtW {
-  float *dw_w, *dw_b, *gn_w, *gn_b;
+  float *dw_w, *dw_b, *gn_w, *gn_b, *dw_wsum;
   Layer conv2, conv3;
 };
 struct ResBlockW {
@@ -332,7 +333,7 @@ struct flm_denoiser : Engine {
   std::vector<Stage> stages;
   Layer proj_out;
   // buffers
-  DevBuf seed_s;
+  DevBuf seed_s, rowstat;
   DevBuf cond_s, spk_s, noise_s, ts_s, x, xb, h, bufU, bufD, bufG, bufA, part, gsc, gof, gctr, ada, sbuf, temb, tfreq, teh,
       cvec, vout;
   DevBuf c_prior, c_mask, c_xq, c_xm, c_h, c_part, c_sc, c_of, c_out;
@@ -347,6 +348,15 @@ struct flm_denoiser : Engine {
     for (int ch = 0; ch < H; ++ch)
       for (int t = 0; t < k; ++t) wt[(size_t)t * H + ch] = w[(size_t)ch * k + t];
     c.dw_w = store.upload(wt);
+    {
+      std::vector<float> ws(H, 0.f);  // response of the conv to a constant input (statistics pivot of the fused kernel)
+      for (int ch = 0; ch < H; ++ch) {
+        double a = 0;
+        for (int t = 0; t < k; ++t) a += w[(size_t)ch * k + t];
+        ws[ch] = (float)a;
+      }
+      c.dw_wsum = store.upload(ws);
+    }
     c.dw_b = store.upload(wm.vec(p + ".conv_1.bias", {H}));
     c.gn_w = store.upload(wm.vec(p + ".ln_1.weight", {H}));
     c.gn_b = store.upload(wm.vec(p + ".ln_1.bias", {H}));
@@ -412,6 +422,52 @@ struct flm_denoiser : Engine {
     proj_out = make_layer(wm.vec("cond_downsampling.proj_out.0.weight", {D, cin}), wm.vec("cond_downsampling.proj_out.0.bias", {D}), cin, D, 1, 0, 1, 1, bf());
   }
 
+  // bf16 mode with a bf16 residual stream: LayerNorm+modulate, depthwise conv and GroupNorm in one kernel, fed by
+  // the row statistics the previous GEMM's epilogue left in `rowstat` (dwconv_fused.cu)
+  bool fused() const { return bf() && h16 && ctx->gemm_gen >= 2 && !getenv("FLAMED_B200_NO_FUSED"); }
+  int rowstat_parts = 0;  // parts written by the last GEMM that produced h
+
+  void ln_dwconv_gn(const ConvNeXtW& c, const float* lnw, const float* lnb, const float* shift, const float* scale, int B,
+                    int L, cudaStream_t s) {
+    DwFused f;
+    memset(&f, 0, sizeof(f));
+    f.h = h.as<bf16>(); f.u = bufU.as<bf16>(); f.g = bufG.as<bf16>();
+    f.rowstat = rowstat.as<float>(); f.parts = rowstat_parts;
+    f.ln_w = lnw; f.ln_b = lnb; f.shift = shift; f.scale = scale; f.mod_bstride = ada_n; f.ln_eps = 1e-6f;
+    f.w = c.dw_w; f.wsum = c.dw_wsum; f.bias = c.dw_b; f.gamma = c.gn_w; f.beta = c.gn_b; f.gn_eps = 1e-5f;
+    f.B = B; f.L = L; f.C = H; f.tma_encode = ctx->tma_encode;
+    const double elems = (double)B * L * H;
+    static const int mode = [] { const char* e = getenv("FLAMED_B200_FUSED_MODE"); return e ? atoi(e) : 2; }();
+    if (mode == 1) {  // cluster kernel: GroupNorm inside
+      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 3), elems * 6);
+      launch_dwconv_fused(f, ctx->num_sms, s);
+      return;
+    }
+    {
+      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
+      launch_dwconv_ln(f, part.as<float>(), ctx->num_sms, s);
+      DwConv dw;
+      memset(&dw, 0, sizeof(dw));
+      dw.io_bf16 = 1; dw.part = part.as<float>(); dw.B = B; dw.L = L; dw.C = H; dw.KW = cfg.kernel_size;
+      dw.gamma = c.gn_w; dw.beta = c.gn_b; dw.eps = 1e-5f; dw.scale = gsc.as<float>(); dw.offset = gof.as<float>();
+      launch_dw_merge(dw, s);
+    }
+    {
+      ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * 2);
+      launch_gn_stream(bufG.p, bufG.p, 1, gsc.as<float>(), gof.as<float>(), B, L, H, s);  // in place: d is still in L2
+    }
+  }
+
+  // conv_2 (GELU) + conv_3 (gated residual with the inner residual u): hres += gate * (u + conv3(gelu(conv2(g))))
+  void convnext_tail(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s) {
+    const int b16 = bf() ? 1 : 0;
+    gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
+    TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
+    p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
+    p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
+    gemm(p, c.conv3, bf(), s);
+  }
+
   // ---- one ConvNeXt: hres += gate * (u + conv3(gelu(conv2(GN(dwconv(u))))))   (prob_generator.py:107-111,162)
   void convnext(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s) {
     const int b16 = bf() ? 1 : 0;
@@ -467,10 +523,16 @@ struct flm_denoiser : Engine {
   void step(int B, int L, int i, float* target, float alpha, cudaStream_t s) {
     const int64_t M = (int64_t)B * L;
     const float* xin = x.as<float>();
+    const bool fz = fused();
     if (bf()) {
       // xb = bf16(x): written by the previous step's Euler epilogue when the loop accumulates into x itself
       if (!xb_fresh) launch_f32_to_bf16(xin, xb.as<bf16>(), M * D, s);
-      gemm(problem(proj_in, xb.p, D, B, L, L, h.p, H, h16 ? 1 : 0, EPI_NONE), proj_in, true, s);
+      TapGemm pi = problem(proj_in, xb.p, D, B, L, L, h.p, H, h16 ? 1 : 0, EPI_NONE);
+      if (fz) {  // the epilogue also leaves the LayerNorm row statistics of h for the first block's fused kernel
+        pi.rowstat = rowstat.as<float>();
+        pi.rowstat_parts = rowstat_parts = tapgemm_tc2_rowstat_parts(pi, ctx->num_sms);
+      }
+      gemm(pi, proj_in, true, s);
     } else {
       gemm(problem(proj_in, xin, D, B, L, L, h.p, H, 0, EPI_NONE), proj_in, false, s);
     }
@@ -479,17 +541,31 @@ struct flm_denoiser : Engine {
     for (size_t k = 0; k < blocks.size(); ++k) {
       const ResBlockW& rb = blocks[k];
       const float* a = arow + k * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m, gate_m
-      ln_modulate(rb.lnc_w, rb.lnc_b, a, a + H, B, L, bufU.p, s);
-      convnext(rb.cn, B, L, a + 2 * H, s);
+      if (fz) {
+        ln_dwconv_gn(rb.cn, rb.lnc_w, rb.lnc_b, a, a + H, B, L, s);
+        convnext_tail(rb.cn, B, L, a + 2 * H, s);
+      } else {
+        ln_modulate(rb.lnc_w, rb.lnc_b, a, a + H, B, L, bufU.p, s);
+        convnext(rb.cn, B, L, a + 2 * H, s);
+      }
       ln_modulate(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
       gemm(problem(rb.mlp0, bufU.p, H, B, L, L, bufA.p, H, b16, EPI_SILU), rb.mlp0, bf(), s);
       TapGemm p = problem(rb.mlp2, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
       p.gate = a + 5 * H; p.gate_bstride = ada_n; p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
+      if (fz) {  // row statistics of the updated h for the next block's (or the final layer's) fused kernel
+        p.rowstat = rowstat.as<float>();
+        p.rowstat_parts = rowstat_parts = tapgemm_tc2_rowstat_parts(p, ctx->num_sms);
+      }
       gemm(p, rb.mlp2, bf(), s);
     }
     const float* a = arow + blocks.size() * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m
-    ln_modulate(nullptr, nullptr, a, a + H, B, L, bufU.p, s);
-    convnext(fin, B, L, a + 2 * H, s);
+    if (fz) {
+      ln_dwconv_gn(fin, nullptr, nullptr, a, a + H, B, L, s);
+      convnext_tail(fin, B, L, a + 2 * H, s);
+    } else {
+      ln_modulate(nullptr, nullptr, a, a + H, B, L, bufU.p, s);
+      convnext(fin, B, L, a + 2 * H, s);
+    }
     ln_modulate(nullptr, nullptr, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
     TapGemm p = problem(conv_out, bufU.p, H, B, L, L, nullptr, D, 0, EPI_EULER);
     p.hres = target; p.ld_res = D; p.alpha = alpha;
@@ -508,6 +584,7 @@ struct flm_denoiser : Engine {
     return bf() && e && std::string(e) == "tensor";
   }
   int launches_per_step() const {  // steady state (the first step of a loop adds the f32 -> bf16 conversion of x0)
+    if (fused()) return 1 + (int)blocks.size() * 6 + 5;  // proj_in + blocks x (fused, 2 GEMMs, LN, 2 GEMMs) + final
     return 1 + (int)blocks.size() * 8 + 7 + ((dw_persistent() || dw_tensor()) ? (int)blocks.size() + 1 : 0);
   }
 
@@ -527,6 +604,7 @@ struct flm_denoiser : Engine {
       moved = true;
       FLM_CUDA(cudaMemset(gctr.p, 0, gctr.bytes));
     }
+    moved |= rowstat.ensure((size_t)M * 32 * 8);  // (sum, sumsq) partials of the rows of h: <= 32 parts (N tile 64)
     moved |= ada.ensure((size_t)nfe * B * ada_n * 4); moved |= sbuf.ensure((size_t)nfe * B * H * e);
     moved |= temb.ensure((size_t)nfe * H * 4); moved |= tfreq.ensure((size_t)nfe * 256 * 4);
     moved |= teh.ensure((size_t)nfe * H * 4); moved |= cvec.ensure((size_t)B * H * 4);
@@ -748,7 +826,20 @@ void run_res_unit(const Engine& e, const ResUnitW& r, void* x, void* t1, void* t
 }
 }  // namespace
 
+// prompt side: residual VQs + timbre transformer (facodec.py:470-507; fvq.py; transformer.py:86-234)
+struct PromptSide {
+  bool present = false;
+  VqPlan plan;
+  int D = 0;
+  struct TLayer { float *ln1w, *ln1b, *ln2w, *ln2b; Layer qkv, out, ffn1, ffn2; };
+  std::vector<TLayer> layers;
+  float *last_w = nullptr, *last_b = nullptr, *pe = nullptr;
+  int pe_rows = 0, heads = 4;
+  DevBuf xt, xa, xn, qkv, att, ffh, qg, pooled_in;
+};
+
 struct flm_codec_dec : Engine {
+  PromptSide prompt;
   Layer timbre_linear, conv0;
   struct Block { ActW act; Layer up; int stride, cin, cout; ResUnitW ru[3]; };
   std::vector<Block> blocks;
@@ -810,10 +901,120 @@ extern "C" int flm_codec_dec_load(flm_ctx* ctx, const flm_tensor* weights, int n
   h->wout = h->store.upload(wt);
   h->bout = wm.vec(pc + ".bias", {1})[0];
   h->cout_final = c;
+  // ---- prompt side (optional: present in FACodecDecoder.state_dict(), not needed by .inference())
+  if (wm.has("quantizer.0.layers.0.in_proj.weight_v") && wm.has("timbre_encoder.last_ln.weight")) {
+    PromptSide& ps = h->prompt;
+    const flm_tensor& wi = wm.get("quantizer.0.layers.0.in_proj.weight_v");  // (cd, D)
+    ps.D = (int)wi.shape[1];
+    ps.plan.n_layers = 0;
+    for (int g = 0; g < 3; ++g) {
+      for (int l = 0;; ++l) {
+        const std::string p = "quantizer." + std::to_string(g) + ".layers." + std::to_string(l);
+        if (!wm.has(p + ".in_proj.weight_v")) break;
+        FLM_REQUIRE(ps.plan.n_layers < VQ_MAX_LAYERS, "too many quantiser layers");
+        const flm_tensor& cbk = wm.get(p + "._codebook.weight");
+        const int ncode = (int)cbk.shape[0], cd = (int)cbk.shape[1];
+        VqLayer& L = ps.plan.layer[ps.plan.n_layers++];
+        L.cd = cd; L.n_codes = ncode; L.group = g;
+        // weight_norm of nn.Linear: norm over dim 1 per output row
+        L.w_in = h->store.upload(fold_weight_norm(wm.vec(p + ".in_proj.weight_g", {cd, 1}), wm.vec(p + ".in_proj.weight_v", {cd, ps.D}), cd));
+        L.b_in = h->store.upload(wm.vec(p + ".in_proj.bias", {cd}));
+        L.w_out = h->store.upload(fold_weight_norm(wm.vec(p + ".out_proj.weight_g", {ps.D, 1}), wm.vec(p + ".out_proj.weight_v", {ps.D, cd}), ps.D));
+        L.b_out = h->store.upload(wm.vec(p + ".out_proj.bias", {ps.D}));
+        std::vector<float> cb = wm.vec(p + "._codebook.weight", {ncode, cd}), cn(cb.size()), sq(ncode);
+        for (int i = 0; i < ncode; ++i) {  // F.normalize(codebook) and its squared norms, in fp32 like the reference
+          float n2 = 0.f;
+          for (int j = 0; j < cd; ++j) n2 += cb[(size_t)i * cd + j] * cb[(size_t)i * cd + j];
+          const float inv = 1.0f / std::max(std::sqrt(n2), 1e-12f);
+          float s2 = 0.f;
+          for (int j = 0; j < cd; ++j) {
+            cn[(size_t)i * cd + j] = cb[(size_t)i * cd + j] * inv;
+            s2 += cn[(size_t)i * cd + j] * cn[(size_t)i * cd + j];
+          }
+          sq[i] = s2;
+        }
+        L.cb = h->store.upload(cb); L.cb_norm = h->store.upload(cn); L.cb_sq = h->store.upload(sq);
+      }
+    }
+    const int D = ps.D;
+    for (int l = 0;; ++l) {
+      const std::string p = "timbre_encoder.layers." + std::to_string(l);
+      if (!wm.has(p + ".ln_1.weight")) break;
+      PromptSide::TLayer t;
+      t.ln1w = h->store.upload(wm.vec(p + ".ln_1.weight", {D})); t.ln1b = h->store.upload(wm.vec(p + ".ln_1.bias", {D}));
+      t.ln2w = h->store.upload(wm.vec(p + ".ln_2.weight", {D})); t.ln2b = h->store.upload(wm.vec(p + ".ln_2.bias", {D}));
+      t.qkv = h->make_layer(wm.vec(p + ".self_attn.in_proj_weight", {3 * D, D}), wm.vec(p + ".self_attn.in_proj_bias", {3 * D}), D, 3 * D, 1, 0, 1, 1, false);
+      t.out = h->make_layer(wm.vec(p + ".self_attn.out_proj.weight", {D, D}), wm.vec(p + ".self_attn.out_proj.bias", {D}), D, D, 1, 0, 1, 1, false);
+      const flm_tensor& f1 = wm.get(p + ".ffn.ffn_1.weight");  // (F, D, k)
+      const int F = (int)f1.shape[0], k = (int)f1.shape[2];
+      t.ffn1 = h->make_layer(pack_conv(wm.vec(p + ".ffn.ffn_1.weight", {F, D, k}), F, D, k), wm.vec(p + ".ffn.ffn_1.bias", {F}), D, F, k, -(k / 2), 1, 1, false);
+      t.ffn2 = h->make_layer(wm.vec(p + ".ffn.ffn_2.weight", {D, F}), wm.vec(p + ".ffn.ffn_2.bias", {D}), F, D, 1, 0, 1, 1, false);
+      ps.layers.push_back(t);
+    }
+    ps.last_w = h->store.upload(wm.vec("timbre_encoder.last_ln.weight", {D}));
+    ps.last_b = h->store.upload(wm.vec("timbre_encoder.last_ln.bias", {D}));
+    const flm_tensor& pe = wm.get("timbre_encoder.position_emb.pe");  // (max_len, 1, D)
+    ps.pe_rows = (int)pe.shape[0];
+    ps.pe = h->store.upload(wm.vec("timbre_encoder.position_emb.pe", {ps.pe_rows, 1, D}));
+    ps.present = true;
+  }
   *out = h.release();
   FLM_API_END
 }
 extern "C" void flm_codec_dec_destroy(flm_codec_dec* h) { delete h; }
+
+// replaces: FACodecDecoder.forward(vq=True) (facodec.py:509-533): quantise the prompt encoder output and pool the timbre.
+// enc_out (B,D,T) f32 in the reference layout -> codes (n_q, B, T) i64, quantized (3, B, D, T) f32 (per quantiser
+// group, nullable), spk (B, D) f32
+extern "C" int flm_codec_dec_prompt(flm_codec_dec* h, const float* enc_out, int B, int T, int64_t* out_codes,
+                                    float* out_quantized, float* out_spk, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(h && enc_out && out_codes && out_spk, "null argument");
+  PromptSide& ps = h->prompt;
+  if (!ps.present) throw Error(FLM_ERR_WEIGHT, "the decoder was loaded without quantizer.* / timbre_encoder.* weights");
+  FLM_REQUIRE(B <= ps.pe_rows, "batch larger than the positional table (the reference indexes it by the batch axis)");
+  DeviceGuard dguard(h->ctx->device);
+  if (B == 0 || T == 0) return FLM_OK;
+  cudaStream_t s = S(stream);
+  const int D = ps.D;
+  const int64_t rows = (int64_t)B * T;
+  const size_t act = (size_t)rows * D * 4;
+  ps.xt.ensure(act); ps.xa.ensure(act); ps.xn.ensure(act); ps.att.ensure(act); ps.qkv.ensure(act * 3);
+  ps.qg.ensure(act * 3);
+  int F = 0;
+  for (auto& t : ps.layers) F = std::max(F, t.ffn1.N);
+  ps.ffh.ensure((size_t)rows * std::max(F, 1) * 4);
+  // x (B,T,D) channels-last, and xa = x + pe[b] (transformer.py:50-52 indexes the table by the BATCH axis)
+  launch_transpose_in(enc_out, B, T, D, ps.xt.as<float>(), ps.pe, ps.xa.as<float>(), s);
+  launch_vq_frames(ps.plan, ps.xt.as<float>(), rows, D, out_codes, ps.qg.as<float>(), s);
+  if (out_quantized)
+    for (int g = 0; g < 3; ++g)
+      launch_transpose_out(ps.qg.as<float>() + (size_t)g * rows * D, B, T, D, out_quantized + (size_t)g * rows * D, s);
+  // pre-LN transformer layers (transformer.py:86-151): x += MHA(LN1(x)); x += ffn_2(relu(conv_k5(LN2(x))))
+  auto ln = [&](const float* w, const float* b, const void* x, void* y) {
+    LnMod l;
+    memset(&l, 0, sizeof(l));
+    l.x = x; l.ldx = D; l.y = y; l.ldy = D; l.w = w; l.b = b; l.eps = 1e-5f; l.rows = rows; l.rows_per_batch = T; l.C = D;
+    l.scale_plus_one = 1.f;
+    launch_ln_mod(l, s);
+  };
+  for (auto& t : ps.layers) {
+    ln(t.ln1w, t.ln1b, ps.xa.p, ps.xn.p);
+    h->gemm(h->problem(t.qkv, ps.xn.p, D, B, T, T, ps.qkv.p, 3 * D, 0, EPI_NONE), t.qkv, false, s);
+    launch_mha_fp32(ps.qkv.as<float>(), B, T, ps.heads, D / ps.heads, ps.att.as<float>(), s);
+    TapGemm po = h->problem(t.out, ps.att.p, D, B, T, T, ps.xa.p, D, 0, EPI_RESID);
+    po.resid_in = ps.xa.p;
+    h->gemm(po, t.out, false, s);
+    ln(t.ln2w, t.ln2b, ps.xa.p, ps.xn.p);
+    h->gemm(h->problem(t.ffn1, ps.xn.p, D, B, T, T, ps.ffh.p, t.ffn1.N, 0, EPI_RELU), t.ffn1, false, s);
+    TapGemm pf = h->problem(t.ffn2, ps.ffh.p, t.ffn1.N, B, T, T, ps.xa.p, D, 0, EPI_RESID);
+    pf.resid_in = ps.xa.p;
+    h->gemm(pf, t.ffn2, false, s);
+  }
+  ln(ps.last_w, ps.last_b, ps.xa.p, ps.xn.p);
+  launch_mean_time(ps.xn.as<float>(), B, T, D, out_spk, s);
+  FLM_API_END
+}
 
 extern "C" int flm_codec_decode(flm_codec_dec* h, const float* latents, const float* spk, int B, int L, float* out_wav,
                                 flm_stream stream) {

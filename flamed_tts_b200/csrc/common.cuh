@@ -166,6 +166,13 @@ struct TapGemm {
   int hres_bf16;
   const void* resid_in;  // EPI_RESID: (B,T_out,N) same storage type as out, row stride ldc
   float alpha;
+  // optional LayerNorm row statistics of the result (tcgen05 CTA-pair kernel, EPI_NONE / EPI_GATE_RESID): every
+  // epilogue thread owns a row and writes (sum, sum of squares) of its share of the columns to
+  // rowstat[row * rowstat_parts + part] (float2; part = n_tile * 2 + column half, fixed order -> deterministic);
+  // the consumer (dwconv_fused) adds the rowstat_parts partials.  *rowstat_parts_out receives the number of parts
+  // of this launch (2 * N / BLOCK_N) on the host.
+  float* rowstat;
+  int rowstat_parts;
 };
 
 // value after bias -> final value; handles every epilogue except the memory side effects

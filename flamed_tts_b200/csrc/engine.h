@@ -23,7 +23,7 @@ enum KClass : int {
   KC_GEMM_TC = 0,   // tcgen05 / TMA tap-GEMM
   KC_GEMM_FMA,      // fp32 FMA tap-GEMM
   KC_LN_MOD,        // LayerNorm + adaLN modulate
-  KC_DWCONV,        // depthwise k=31 + GroupNorm partial statistics
+  KC_DWCONV,        // depthwise k=31 + GroupNorm partial statistics (fp32 mode) / the fused LN + dwconv + GN kernel
   KC_GN_FINALIZE,
   KC_GN_APPLY,
   KC_ACT1D,         // anti-aliased Snake activation

@@ -18,6 +18,7 @@ void tapgemm_tc_init();
 void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream);
 bool tapgemm_tc2_supported(const TapGemm& p);
 void tapgemm_tc2_init();
+int tapgemm_tc2_rowstat_parts(const TapGemm& p, int num_sms);  // partials per row written when p.rowstat != null
 void kernels_norm_init();
 
 // ---- row-wise LayerNorm (+ adaLN modulate): one warp per row, C % 128 == 0, C <= 1024
@@ -58,6 +59,29 @@ void launch_dwconv_tc(const DwConv& p, int num_sms, cudaStream_t stream);
 bool dwconv_tc_supported(const DwConv& p);
 void dwconv_tc_init();
 void launch_dw_merge(const DwConv& p, cudaStream_t stream);
+
+// ---- ConvNeXt front half in one kernel (dwconv_fused.cu, bf16 mode with a bf16 residual stream):
+//      u = LN(h)*(1+scale)+shift, d = dwconv31(u)+bias, g = GroupNorm(C,C)(d) over the whole time axis
+struct DwFused {
+  const bf16* h;  // (B,L,C) residual stream = LayerNorm input
+  bf16* u;        // (B,L,C) out: modulated LayerNorm output (inner residual of the ConvNeXt block)
+  bf16* g;        // (B,L,C) out: normalised depthwise-conv output (input of conv_2)
+  const float* rowstat; int parts;  // (B*L, parts) float2 (sum, sumsq) partials of the rows of h (TapGemm::rowstat)
+  const float* ln_w; const float* ln_b;  // LayerNorm affine (nullable: FinalLayer's LN has none)
+  const float* shift; const float* scale; int64_t mod_bstride;  // adaLN modulation of sample b (nullable)
+  float ln_eps;
+  const float* w;     // (31, C) tap-major depthwise weights
+  const float* wsum;  // (C) sum over the taps
+  const float* bias;  // (C)
+  const float* gamma; const float* beta; float gn_eps;  // GroupNorm affine
+  int B, L, C;
+  void* tma_encode;
+};
+void launch_dwconv_fused(const DwFused& p, int num_sms, cudaStream_t stream);
+void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t stream);
+bool dwconv_fused_supported(const DwFused& p);
+int dwconv_fused_cluster(int B, int L, int C, int num_sms);
+void dwconv_fused_init();
 
 // ---- generic grouped statistics over (rows x channels-in-group) for GroupNorm(G) in the cond
 //      down-sampler: partials (B, nchunk, G, 2) from chunks of GS_ROWS rows
@@ -151,5 +175,31 @@ void launch_conv_in_wav(const float* wav, const float* w, const float* bias, int
                         cudaStream_t stream);
 // (B,T,C) -> (B,C,T)
 void launch_transpose_out(const float* x, int B, int T, int C, float* y, cudaStream_t stream);
+
+// ---- prompt side of the FaCodec decoder (prompt_side.cu): residual vector quantisers + timbre transformer pieces
+constexpr int VQ_MAX_LAYERS = 8;
+constexpr int VQ_MAX_CD = 16;
+struct VqLayer {
+  const float* w_in;     // (cd, D) weight-norm folded in_proj
+  const float* b_in;     // (cd)
+  const float* cb;       // (n_codes, cd) codebook
+  const float* cb_norm;  // (n_codes, cd) F.normalize(codebook)
+  const float* cb_sq;    // (n_codes) |normalised code|^2
+  const float* w_out;    // (D, cd) weight-norm folded out_proj
+  const float* b_out;    // (D)
+  int cd, n_codes, group;  // group 0 / 1 quantise x, group 2 quantises x - (q0 + q1)
+};
+struct VqPlan {
+  VqLayer layer[VQ_MAX_LAYERS];
+  int n_layers;
+};
+// x (rows, D) channels-last -> codes (n_layers, rows) int64, qgroups (3, rows, D) summed quantised vectors per group
+void launch_vq_frames(const VqPlan& plan, const float* x, int64_t rows, int D, int64_t* codes, float* qgroups,
+                      cudaStream_t stream);
+// (B,C,T) -> (B,T,C); y_pe (nullable) = the same + pe[b, :] broadcast over T
+void launch_transpose_in(const float* x, int B, int T, int C, float* y, const float* pe, float* y_pe, cudaStream_t stream);
+// fp32 multi-head self-attention without a mask: qkv (B,T,3*H*DH) -> out (B,T,H*DH), DH 32 or 64
+void launch_mha_fp32(const float* qkv, int B, int T, int H, int DH, float* out, cudaStream_t stream);
+void launch_mean_time(const float* x, int B, int T, int C, float* y, cudaStream_t stream);
 
 }  // namespace flm

@@ -411,6 +411,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait_cluster(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
+      f32x2 st_s = 0ull, st_q = 0ull;  // LayerNorm row statistics of this thread's columns of the tile (p.rowstat)
 #pragma unroll 1
       for (int s = 0; s < SLABS; ++s) {
         const int n = nt * BLOCK_N + s * SLAB_COLS + half * 32;
@@ -468,6 +469,10 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               } else {
                 r2 = add2(h2, a2[c * 4 + j]);
               }
+              if (EPI == EPI_GATE_RESID && p.rowstat) {
+                st_s = add2(st_s, r2);
+                st_q = fma2(r2, r2, st_q);
+              }
               float lo, hi;
               unpack2(r2, lo, hi);
               __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -476,6 +481,14 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             *slot = make_uint4(o[0], o[1], o[2], o[3]);
           }
         } else {
+#pragma unroll
+          if (EPI == EPI_NONE && p.rowstat) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              st_s = add2(st_s, a2[i]);
+              st_q = fma2(a2[i], a2[i], st_q);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) unpack2(a2[i], v[2 * i], v[2 * i + 1]);
           act_fast32<EPI>(v);
@@ -492,6 +505,25 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
+      if ((EPI == EPI_NONE || EPI == EPI_GATE_RESID) && p.rowstat) {
+        // global row of this thread (rows the TMA store clips are skipped)
+        int64_t grow;
+        bool ok;
+        if (sch.flatten) {
+          grow = (int64_t)mt * BLOCK_M + rrow;
+          ok = grow < (int64_t)p.B * p.T_out;
+        } else {
+          const int tb = mt / sch.tiles_m_per_b, tr = (mt % sch.tiles_m_per_b) * BLOCK_M + rrow;
+          grow = (int64_t)tb * p.T_out + tr;
+          ok = tb < p.B && tr < p.T_out;
+        }
+        if (ok) {
+          float s0, s1, q0, q1;
+          unpack2(st_s, s0, s1);
+          unpack2(st_q, q0, q1);
+          *reinterpret_cast<float2*>(p.rowstat + (grow * p.rowstat_parts + nt * 2 + half) * 2) = make_float2(s0 + s1, q0 + q1);
+        }
+      }
     }
   } else if (warp == 2 + NUM_EPI_WARPS) {
     // ===================== epilogue operand loader =====================
@@ -623,6 +655,17 @@ bool tapgemm_tc2_supported(const TapGemm& p) {
   }
 }
 
+// number of (sum, sumsq) partials per row the epilogue of this problem writes: 2 per N tile
+int tapgemm_tc2_rowstat_parts(const TapGemm& p, int num_sms) {
+  const bool flatten = p.ntaps == 1 && p.off0 == 0;
+  const int64_t rows_total = (int64_t)p.B * p.T_out;
+  const int mt = flatten ? (int)((rows_total + BLOCK_M - 1) / BLOCK_M) : ((p.T_out + BLOCK_M - 1) / BLOCK_M) * p.B;
+  const int mpairs = (mt + 1) / 2;
+  int BN = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0 ? 128 : 64);
+  while (BN > 64 && p.N % (BN / 2) == 0 && (int64_t)mpairs * (p.N / BN) < num_sms / 2) BN /= 2;
+  return 2 * (p.N / BN);
+}
+
 void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStream_t stream) {
   FLM_REQUIRE(tapgemm_tc2_supported(p), "tapgemm_tc2: unsupported problem");
   FLM_REQUIRE(tma_encode != nullptr, "tapgemm_tc2: cuTensorMapEncodeTiled entry point not resolved");
@@ -644,6 +687,7 @@ void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStr
   while (BN > 64 && p.N % (BN / 2) == 0 && (int64_t)mpairs * (p.N / BN) < num_sms / 2) BN /= 2;
   sch.num_n_tiles = p.N / BN;
   sch.num_tiles = mpairs * sch.num_n_tiles;
+  FLM_REQUIRE(!p.rowstat || p.rowstat_parts == 2 * sch.num_n_tiles, "tapgemm_tc2: rowstat_parts must be tapgemm_tc2_rowstat_parts(p)");
   sch.stages = 0; sch.nbuf = 0;
   CUtensorMap tm[5];
   memset(tm, 0, sizeof(tm));

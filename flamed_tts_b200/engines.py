@@ -245,10 +245,12 @@ class CodecDecoderEngine:
 
     def __init__(self, ctx, state_dict, precision="bf16"):
         self.ctx, self.lib = ctx, ctx.lib
-        named = [(k, v) for k, v in state_dict.items() if k.startswith("model.") or k.startswith("timbre_linear.")]
+        named = [(k, v) for k, v in state_dict.items() if k.split(".")[0] in ("model", "timbre_linear", "quantizer",
+                                                                              "timbre_encoder")]
         arr, n, keep = pack_weights(named)
         self.handle = c_void_p()
         check(self.lib.flm_codec_dec_load(ctx.handle, arr, n, _mode(precision), byref(self.handle)))
+        self.n_q = len([k for k in state_dict if k.startswith("quantizer.") and k.endswith("._codebook.weight")])
 
     def __del__(self):
         if getattr(self, "handle", None):
@@ -264,6 +266,18 @@ class CodecDecoderEngine:
         wav = torch.empty((B, 1, L * hop), device=dev, dtype=torch.float32)
         check(self.lib.flm_codec_decode(self.handle, _ptr(latents_bld), _ptr(spk), B, L, _ptr(wav), self.ctx.stream()))
         return wav
+
+    def prompt(self, enc_out):
+        """FACodecDecoder.forward(vq=True): enc_out (B,256,T) -> codes (n_q,B,T) i64, quantized (3,B,256,T), spk (B,256)"""
+        dev = self.ctx.device
+        enc_out = _f32(enc_out, dev)
+        B, D, T = enc_out.shape
+        codes = torch.empty((self.n_q, B, T), device=dev, dtype=torch.int64)
+        quant = torch.empty((3, B, D, T), device=dev, dtype=torch.float32)
+        spk = torch.empty((B, D), device=dev, dtype=torch.float32)
+        check(self.lib.flm_codec_dec_prompt(self.handle, _ptr(enc_out), B, T, _ptr(codes), _ptr(quant), _ptr(spk),
+                                            self.ctx.stream()))
+        return codes, quant, spk
 
     def activation(self, prefix, x_btc):
         dev = self.ctx.device

@@ -161,6 +161,15 @@ int flm_codec_decode(flm_codec_dec* h, const float* latents, const float* spk, i
 int flm_codec_dec_activation(flm_codec_dec* h, const char* prefix, const float* x, int B, int T, int C, float* y,
                              flm_stream stream);
 
+/* replaces: FACodecDecoder.forward(vq=True), facodec.py:509-533 (quantize 470-507: three residual VQs of factorised
+ *           layers, quantize/fvq.py:35-116, quantize/rvq.py:27-73; timbre transformer transformer.py:86-234) - the
+ *           prompt side.  Needs the `quantizer.*` and `timbre_encoder.*` keys at load time.
+ * enc_out (B,256,T) f32 in the REFERENCE layout (the encoder's output); out_codes (n_q = 6, B, T) i64;
+ * out_quantized (3, B, 256, T) f32 = summed quantised vectors of the prosody / content / residual groups (nullable);
+ * out_spk (B,256) f32 = mean over time of the timbre encoder's output.  fp32 FMA throughout. */
+int flm_codec_dec_prompt(flm_codec_dec* h, const float* enc_out, int B, int T, int64_t* out_codes, float* out_quantized,
+                         float* out_spk, flm_stream stream);
+
 /* ---------------------------------------------------------------- FaCodec encoder (prompt)
  * replaces: FACodecEncoder.forward, facodec.py:215-217 (ctor 183-213, EncoderBlock 136-155). */
 int flm_codec_enc_load(flm_ctx* ctx, const flm_tensor* weights, int n, flm_codec_enc** out);

@@ -344,3 +344,34 @@ def test_wav_to_pcm16(ctx):
         got = wav_to_pcm16(ctx, w.to(DEV)).cpu()
         want = torch.clamp(torch.round(w * 32767.0), -32768, 32767).to(torch.int16)
         assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------ prompt side (f3)
+def test_prompt_side_codes_bit_exact_and_timbre(dropin, codec_dec_sd, golden_dir):
+    """FACodecDecoder.forward(vq=True) through flm_codec_dec_prompt: the six code streams of the reference fixture bit
+    exact (a code may differ only where the two best cosine similarities are within 1e-6: reported, none expected),
+    timbre vector <= 2e-5, quantised sums <= 1e-5; and against the oracle on a larger seeded batch (B=3, T=173)"""
+    _, dec = dropin
+    dec.set_precision("fp32")
+    g = np.load(os.path.join(golden_dir, "codec_encode.npz"))
+    enc_out = torch.from_numpy(g["enc_out"])
+    outs, codes, commit, bufs, spk = dec(enc_out.to(DEV), eval_vq=False, vq=True)
+    assert codes.dtype == torch.int64 and list(codes.shape) == list(g["codes"].shape)
+    assert torch.equal(codes.cpu(), torch.from_numpy(g["codes"]))
+    assert _rel(spk, torch.from_numpy(g["timbre"])) < 2e-5
+    assert len(bufs) == 3 and list(outs.shape) == [1, 256, enc_out.shape[-1]] and list(commit.shape) == [6, 1]
+    torch.manual_seed(12)
+    x = torch.randn(3, 256, 173)
+    with torch.inference_mode():
+        o_codes, o_spk = O.codec_prompt_features(codec_dec_sd, x)
+        q0, _ = O._rvq(codec_dec_sd, "quantizer.0", x, 1)
+        q1, _ = O._rvq(codec_dec_sd, "quantizer.1", x, 2)
+        q2, _ = O._rvq(codec_dec_sd, "quantizer.2", x - (q0 + q1), 3)
+    outs, codes, _, bufs, spk = dec(x.to(DEV), eval_vq=False, vq=True)
+    diff = codes.cpu() != o_codes
+    print("prompt codes differing from the oracle: %d of %d" % (int(diff.sum()), diff.numel()))
+    assert int(diff.sum()) <= 2  # near-ties of the cosine argmax only
+    if not diff.any():
+        assert _rel(bufs[0], q0) < 1e-5 and _rel(bufs[1], q1) < 1e-5 and _rel(bufs[2], q2) < 1e-5
+        assert _rel(outs, q0 + q1 + q2) < 1e-5
+    assert _rel(spk, o_spk) < 2e-5

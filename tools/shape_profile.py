@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Per-(kernel class, shape) device time of one bench bucket (CUDA events around every launch).
-env: BATCH (bucket index, default 3 = longest), NFE (default 8)."""
+"""Per-(kernel class, shape) device time of one bench back-bucket (CUDA events around every launch).
+env: NFE (denoiser steps, default 8), UTTS (pool size, default 256), BUCKET (which front bucket, default 0 = longest)."""
 import os
 import sys
 
@@ -10,25 +10,22 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from flamed_tts_b200.engines import Context  # noqa: E402
 
-
-class A:
-    utterances, max_batch = 256, 64
-    nsteps_durgen, nsteps_denoiser, temp_durgen, temp_denoiser = 16, int(os.environ.get("NFE", 8)), 0.3, 0.3
-
-
+args = bench.parse_args(["--nsteps-denoiser", os.environ.get("NFE", "8"), "--utterances", os.environ.get("UTTS", "256")])
 dev = torch.device("cuda:0")
 cfg, model, enc, dec = bench.build_models(dev, "bf16")
-model.set_noise_device("cuda")
+model.set_noise_device("philox")
 model.prob_generator.use_cuda_graph = False
-wl, batches = bench.make_batches(A, 0, model, enc, dec, dev)
-sel = [batches[int(os.environ.get("BATCH", len(batches) - 1))]]
+wl, n = bench.global_workload(args, 1)
+codes, timbres = bench.prompt_codes(wl, enc, dec, dev)
+batches = bench.host_batches(wl, bench.rank_share(args, wl, 0, 1), codes, timbres)
+sel = [batches[int(os.environ.get("BUCKET", 0))]]
 for b in sel:
     b["dev"] = {k: b[k].to(dev) for k in ("phonemes", "src_lens", "prompts", "timbres")}
 ctx = Context.get(dev)
 for rep in range(2):
     ctx.profile(rep == 1)
     torch.manual_seed(0)
-    bench.run_step(model, dec, sel, A, dev, False)
+    bench.run_step(model, dec, sel, args, dev, False)
     torch.cuda.synchronize()
 rows = ctx.profile_detail()
 ctx.profile(False)
