@@ -22,6 +22,8 @@
 // outputs / fp32 residual streams / the Euler update stay on the first-generation kernel (tapgemm_tc.cu).
 #include <cuda.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -619,16 +621,50 @@ void set_attr_all() {
   set_attr_one<BLOCK_N, EPI_RELU>(); set_attr_one<BLOCK_N, EPI_RESID>(); set_attr_one<BLOCK_N, EPI_GATE_RESID>();
 }
 
+// A tensor map is a pure function of (base pointer, dims, strides, box, swizzle, L2 promotion): the loop re-launches
+// the same few dozen (pointer, shape) combinations tens of thousands of times per step, so the encoded maps are kept
+// (per host thread; bounded) instead of calling cuTensorMapEncodeTiled five times per launch.
+struct MapKey {
+  const void* base;
+  uint64_t d0, d1, d2, s0, s1;
+  uint32_t b0, b1, b2, rank, promo;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s0 == o.s0 && s1 == o.s1 && b0 == o.b0 &&
+           b1 == o.b1 && b2 == o.b2 && rank == o.rank && promo == o.promo;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.d0, k.d1, k.d2, k.s0, k.s1, (uint64_t)k.b0 << 32 | k.b1, (uint64_t)k.b2 << 40 | (uint64_t)k.rank << 8 | k.promo})
+      h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+    return (size_t)h;
+  }
+};
+CUtensorMap cached_map(EncodeTiledFn encode, uint32_t rank, const void* base, const cuuint64_t* dims,
+                       const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey k{base, dims[0], dims[1], rank > 2 ? dims[2] : 1, strides[0], rank > 2 ? strides[1] : 0, box[0], box[1],
+           rank > 2 ? box[2] : 1, rank, (uint32_t)promo};
+  auto it = cache.find(k);
+  if (it != cache.end()) return it->second;
+  CUtensorMap tm;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(-2, std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r));
+  if (cache.size() >= 4096) cache.clear();
+  cache.emplace(k, tm);
+  return tm;
+}
+
 // 3-D bf16 map (cols, rows-per-sample, samples) with a (64 x 128 x 1) SWIZZLE_128B box over a row-major tensor
 void encode_slab_map(EncodeTiledFn encode, CUtensorMap* tm, const void* base, int64_t ld, int N, int rows, int nb,
                      const char* what) {
   cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows, (cuuint64_t)nb};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rows};
-  cuuint32_t box[3] = {(cuuint32_t)SLAB_COLS, (cuuint32_t)BLOCK_M, 1}, estr[3] = {1, 1, 1};
-  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw Error(-2, std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r));
+  cuuint32_t box[3] = {(cuuint32_t)SLAB_COLS, (cuuint32_t)BLOCK_M, 1};
+  *tm = cached_map(encode, 3, base, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, what);
 }
 
 }  // namespace
@@ -693,24 +729,18 @@ void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStr
   memset(tm, 0, sizeof(tm));
   {
     cuuint64_t dims[3], strides[2];
-    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M, 1}, estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M, 1};
     if (sch.flatten) { dims[0] = (cuuint64_t)p.K; dims[1] = (cuuint64_t)p.B * p.T_in; dims[2] = 1; }
     else { dims[0] = (cuuint64_t)p.K; dims[1] = (cuuint64_t)p.T_in; dims[2] = (cuuint64_t)p.B; }
     strides[0] = (cuuint64_t)p.lda * 2;
     strides[1] = (cuuint64_t)p.lda * 2 * dims[1];
-    CUresult r = encode(&tm[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.A), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r));
+    tm[0] = cached_map(encode, 3, p.A, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "A");
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.ntaps * p.N};
     cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(BN / 2)}, estr[2] = {1, 1};
-    CUresult r = encode(&tm[1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.W), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(W) failed: " + std::to_string((int)r));
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(BN / 2)};
+    tm[1] = cached_map(encode, 2, p.W, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "W");
   }
   const int rows = sch.flatten ? (int)rows_total : p.T_out, nb = sch.flatten ? 1 : p.B;
   if (p.epi == EPI_GATE_RESID) {
