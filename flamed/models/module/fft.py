@@ -6,7 +6,6 @@ checkpoints load unchanged (flamed/models/module/transformer/{Models,Layers,SubL
 the math is restated with fused attention (F.scaled_dot_product_attention) instead of
 materialised (heads*B, L, L) score tensors.
 """
-import os
 
 import numpy as np
 import torch
@@ -18,8 +17,6 @@ from flamed.text.symbols import symbols
 
 try:  # library attention kernel with per-sample key lengths (flash-attn); optional
     from flash_attn import flash_attn_with_kvcache as _flash_kvcache
-    if os.environ.get("FLAMED_B200_ATTN", "flash") != "flash":
-        _flash_kvcache = None
 except Exception:  # noqa: BLE001
     _flash_kvcache = None
 

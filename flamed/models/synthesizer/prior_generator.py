@@ -5,8 +5,6 @@ parameter names).  Only `pva` is on the B200 kernel path; the FFT stacks are PyT
  and run under bf16 autocast when the model precision is 'bf16'
 (the phoneme encoder always stays fp32: rounded durations must match the reference).
 """
-import os
-
 import torch
 import torch.nn as nn
 
@@ -88,7 +86,7 @@ class PriorGenerator(nn.Module):
     def decode_priors(self, x, tgt_lens, prompts, prompts_len, bf16=False, want_logits=True):
         """length-regulated encoder output (B,L,192) -> (embs, logits, tgt_mask); prior_generator.py:162-181.
         want_logits=False returns None for the logits (see logits_from)."""
-        fast = bf16 and x.is_cuda and os.environ.get("FLAMED_B200_FFT", "kernels") != "torch"
+        fast = bf16 and x.is_cuda
         self.shared_decoder.b200 = fast
         for d in self.prior_decoder:
             d.b200 = fast

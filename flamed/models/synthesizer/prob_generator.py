@@ -6,8 +6,6 @@ fold/down-sampler, the N-step Euler loop and every block inside it run in sm_100
 (tcgen05 GEMMs + fused memory-bound kernels, one CUDA graph per (B, L, nfe)) behind
 flm_cond_prepare / flm_denoiser_sample.
 """
-import os
-
 import torch
 import torch.nn as nn
 
@@ -92,7 +90,7 @@ class ProbGenerator(EngineOwner):
         # True / False / "auto": one CUDA graph per (B, L, nfe) pays off when the kernels are short
         # (launch-bound, few frames); big batches are launched directly (kernels of ~100 us hide the launches)
         self.use_cuda_graph = "auto"
-        self.graph_max_rows = int(os.environ.get("FLAMED_B200_GRAPH_MAX_ROWS", 16384))
+        self.graph_max_rows = 16384
 
     def _build_engine(self, ctx):
         from flamed_tts_b200.engines import DenoiserEngine

@@ -52,9 +52,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
     throw Error(FLM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   tapgemm_tc_init();
   tapgemm_tc2_init();
-  dwconv_tc_init();
   dwconv_fused_init();
-  if (const char* g = getenv("FLAMED_B200_GEMM")) c->gemm_gen = atoi(g) == 1 ? 1 : 2;
   kernels_norm_init();
   *out = c.release();
   FLM_API_END
@@ -321,7 +319,7 @@ struct ResBlockW {
 struct flm_denoiser : Engine {
   flm_prob_cfg cfg;
   int H, D, ada_n;
-  bool h16 = false;  // bf16 residual stream inside a step (FLM_BF16 mode; opt-out: FLAMED_B200_RESIDUAL=fp32)
+  bool h16 = false;  // bf16 residual stream inside a step (FLM_BF16 mode); fp32 stream in the FLM_F32 parity mode
   size_t hsize() const { return h16 ? 2 : 4; }
   // denoiser weights
   Layer time0, time2, cond_embed, proj_in, ada_all, conv_out;
@@ -424,7 +422,7 @@ struct flm_denoiser : Engine {
 
   // bf16 mode with a bf16 residual stream: LayerNorm+modulate, depthwise conv and GroupNorm in one kernel, fed by
   // the row statistics the previous GEMM's epilogue left in `rowstat` (dwconv_fused.cu)
-  bool fused() const { return bf() && h16 && ctx->gemm_gen >= 2 && !getenv("FLAMED_B200_NO_FUSED"); }
+  bool fused() const { return bf(); }
   int rowstat_parts = 0;  // parts written by the last GEMM that produced h
 
   void ln_dwconv_gn(const ConvNeXtW& c, const float* lnw, const float* lnb, const float* shift, const float* scale, int B,
@@ -437,12 +435,6 @@ struct flm_denoiser : Engine {
     f.w = c.dw_w; f.wsum = c.dw_wsum; f.bias = c.dw_b; f.gamma = c.gn_w; f.beta = c.gn_b; f.gn_eps = 1e-5f;
     f.B = B; f.L = L; f.C = H; f.tma_encode = ctx->tma_encode;
     const double elems = (double)B * L * H;
-    static const int mode = [] { const char* e = getenv("FLAMED_B200_FUSED_MODE"); return e ? atoi(e) : 2; }();
-    if (mode == 1) {  // cluster kernel: GroupNorm inside
-      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 3), elems * 6);
-      launch_dwconv_fused(f, ctx->num_sms, s);
-      return;
-    }
     {
       ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
       launch_dwconv_ln(f, part.as<float>(), ctx->num_sms, s);
@@ -468,34 +460,25 @@ struct flm_denoiser : Engine {
     gemm(p, c.conv3, bf(), s);
   }
 
-  // ---- one ConvNeXt: hres += gate * (u + conv3(gelu(conv2(GN(dwconv(u))))))   (prob_generator.py:107-111,162)
+  // ---- one ConvNeXt in the fp32 parity mode: hres += gate * (u + conv3(gelu(conv2(GN(dwconv(u))))))
+  //      (prob_generator.py:107-111,162); the depthwise kernel finalises the GroupNorm statistics itself
   void convnext(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s) {
-    const int b16 = bf() ? 1 : 0;
     DwConv dw;
-    dw.x = bufU.p; dw.y = bufD.p; dw.io_bf16 = b16; dw.w = c.dw_w; dw.bias = c.dw_b; dw.part = part.as<float>();
+    memset(&dw, 0, sizeof(dw));
+    dw.x = bufU.p; dw.y = bufD.p; dw.io_bf16 = 0; dw.w = c.dw_w; dw.bias = c.dw_b; dw.part = part.as<float>();
     dw.B = B; dw.L = L; dw.C = H; dw.KW = cfg.kernel_size;
     dw.gamma = c.gn_w; dw.beta = c.gn_b; dw.eps = 1e-5f; dw.scale = gsc.as<float>(); dw.offset = gof.as<float>();
     dw.counters = gctr.as<int>();
-    dw.tma_encode = dw_persistent() ? ctx->tma_encode : nullptr;
     const double elems = (double)B * L * H, eb = (double)esize();
     {
       ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * cfg.kernel_size, elems * 2 * eb);
-      if (dw_tensor() && dwconv_tc_supported(dw)) {
-        launch_dwconv_tc(dw, ctx->num_sms, s);
-        launch_dw_merge(dw, s);
-      } else {
-        launch_dwconv(dw, s);
-      }
+      launch_dwconv(dw, s);
     }
     {
       ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * eb);
-      launch_gn_stream(bufD.p, bufG.p, b16, gsc.as<float>(), gof.as<float>(), B, L, H, s);
+      launch_gn_stream(bufD.p, bufG.p, 0, gsc.as<float>(), gof.as<float>(), B, L, H, s);
     }
-    gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
-    TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
-    p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
-    p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
-    gemm(p, c.conv3, bf(), s);
+    convnext_tail(c, B, L, gate, s);
   }
 
   void ln_modulate(const float* w, const float* b, const float* shift, const float* scale, int B, int L, void* y,
@@ -574,18 +557,10 @@ struct flm_denoiser : Engine {
     gemm(p, conv_out, bf(), s);
   }
   bool xb_fresh = false;  // xb holds bf16(x) of the current state
-  // the persistent depthwise kernel (bf16 mode) is followed by its statistics-merge kernel: +1 per ConvNeXt
-  bool dw_persistent() const { return bf() && !getenv("FLAMED_B200_DWCONV_V1"); }
-  // experimental tensor-core depthwise conv (dwconv_tc.cu), opt-in with FLAMED_B200_DWCONV=tensor: parity-green but
-  // measured 2.2x SLOWER than the FP32-FMA kernel on B200 (0.37 vs 0.17 ms at 79k frames): with N=16 every MMA
-  // re-reads its 4 KB A operand from shared memory, so the kernel is shared-memory-bandwidth bound
-  bool dw_tensor() const {
-    const char* e = getenv("FLAMED_B200_DWCONV");
-    return bf() && e && std::string(e) == "tensor";
-  }
   int launches_per_step() const {  // steady state (the first step of a loop adds the f32 -> bf16 conversion of x0)
-    if (fused()) return 1 + (int)blocks.size() * 6 + 5;  // proj_in + blocks x (fused, 2 GEMMs, LN, 2 GEMMs) + final
-    return 1 + (int)blocks.size() * 8 + 7 + ((dw_persistent() || dw_tensor()) ? (int)blocks.size() + 1 : 0);
+    // bf16: proj_in + per block (LN-fused depthwise conv, statistics merge, GroupNorm apply, 2 GEMMs, LN, 2 GEMMs)
+    if (fused()) return 1 + (int)blocks.size() * 8 + 7;
+    return 1 + (int)blocks.size() * 8 + 7;  // fp32: proj_in + per block (LN, dwconv, GN apply, 2 GEMMs, LN, 2 GEMMs)
   }
 
   bool ensure(int B, int L, int nfe) {
@@ -624,12 +599,9 @@ extern "C" int flm_denoiser_load(flm_ctx* ctx, const flm_tensor* weights, int n,
   WeightMap wm(weights, n);
   std::unique_ptr<flm_denoiser> h(new flm_denoiser(ctx, mode));
   h->cfg = *cfg;
-  {
-    const char* r = getenv("FLAMED_B200_RESIDUAL");
-    // bf16 residual stream by default in the throughput mode (128-step latents stay at 2.8e-3 rel-L2 of the
-    // fp32 reference, same as with an fp32 stream); FLAMED_B200_RESIDUAL=fp32 restores the fp32 stream
-    h->h16 = mode == FLM_BF16 && !(r && std::string(r) == "fp32");
-  }
+  // the throughput mode keeps the residual stream of a step in bf16 (128-step latents stay at 2.8e-3 rel-L2 of the
+  // fp32 reference, 2.5e-3 with an fp32 stream); the ODE state x_t itself is fp32 in both modes
+  h->h16 = mode == FLM_BF16;
   h->load(wm);
   *out = h.release();
   FLM_API_END
@@ -1317,7 +1289,7 @@ extern "C" int flm_conv1d_bf16(flm_ctx* ctx, const void* A, const void* W, const
   tag[0] = 0;
   if (ctx->prof_on) snprintf(tag, sizeof(tag), "K%d N%d taps%d epi%d B%d T%d", K, N, ntaps, epi, B, T);
   ProfScope ps(ctx, KC_GEMM_TC, S(stream), 2.0 * M * N * K * ntaps, M * K * 2 + (double)ntaps * N * K * 2 + M * N * 2, tag);
-  if (ctx->gemm_gen >= 2 && tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, S(stream));
+  if (tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, S(stream));
   else launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, S(stream));
   FLM_API_END
 }
@@ -1378,7 +1350,7 @@ extern "C" int flm_tapgemm_bench(flm_ctx* ctx, int mode, int B, int T, int K, in
   FLM_CUDA(cudaEventCreate(&e1));
   auto launch = [&]() {
     if (mode == FLM_BF16) {
-      if (ctx->gemm_gen >= 2 && tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, s);
+      if (tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, s);
       else launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
     } else {
       launch_tapgemm_simt(p, s);

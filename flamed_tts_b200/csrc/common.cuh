@@ -5,6 +5,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -117,6 +119,30 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   f32x2 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// ---- programmatic dependent launch: a kernel launched with launch_pdl() may start while the previous kernel in the
+// stream is still draining its last wave; everything it does before pdl_wait() (barrier / TMEM / descriptor set-up,
+// constant-weight loads) overlaps that tail, pdl_wait() returns once the previous grid has completed and its writes
+// are visible.  pdl_trigger() (at the top of a kernel) lets ITS successor do the same.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("FLAMED_B200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  FLM_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,26 +1,30 @@
-// ConvNeXt front half of the denoiser in ONE kernel (bf16 throughput mode):
+// LayerNorm + adaLN modulate fused into the depthwise conv of the ConvNeXt block (bf16 throughput mode):
 //
 //     u = LayerNorm(h) * (1 + scale_b) + shift_b          (prob_generator.py:136,162 / 229,257: ln_conv + modulate)
 //     d = depthwise_conv31(u) + bias                       (prob_generator.py:81-88,108: conv_1, zero padded)
-//     g = GroupNorm(C, C)(d)  over the whole time axis     (prob_generator.py:89,109: ln_1)
+//     + per-(sample, 32-frame chunk, channel) partial statistics of d for GroupNorm(C, C) (prob_generator.py:89,109)
 //
-// Before this kernel the three steps were four launches (ln_mod, dwconv + partial statistics, statistics merge,
-// streaming GroupNorm apply) moving 12 B per element through HBM; here h is read once (2 B), u is written once (2 B,
-// conv_3's epilogue needs it as the inner residual) and g is written once (2 B).
+// Before this kernel u was produced by a separate LayerNorm pass (read h, write u: 4 B per element through HBM) and read
+// again by the conv; here h is read once, u is written once (conv_3's epilogue needs it as the inner residual) and the
+// un-normalised d is written once; the statistics merge and the in-place streaming GroupNorm apply stay separate
+// launches (kernels_norm.cu).
 //
 //   * LayerNorm needs full-row statistics (1024 channels) while a block owns 256 channels: the row sums come from the
 //     epilogue of the GEMM that produced h (TapGemm::rowstat, (sum, sumsq) partials per row), so normalising is two
 //     FFMA2 per loaded element pair:  u = (x * rstd_r - mean_r * rstd_r) * A_c + B_c  with the per-sample affine
 //     A = w (1 + scale), B = b (1 + scale) + shift held in registers.
-//   * GroupNorm needs per-(sample, channel) statistics over ALL frames before the first output can be normalised.
-//     A thread-block cluster of S CTAs owns one (sample, 256-channel block): each CTA convolves a contiguous range of
-//     32-frame chunks (3-deep TMA ring, 31-tap FFMA2 sliding window as in the previous kernel), keeps the running
-//     (sum, sum of squares) of its channels in registers, writes the un-normalised d; the S partial statistics are
-//     exchanged through distributed shared memory (fixed order: deterministic), and every CTA then normalises ITS OWN
-//     rows in place.  Those rows were written microseconds earlier by the same SM and are still in L2 (a few hundred
-//     KB per CTA), so the second pass costs L2 bandwidth, not HBM bandwidth.
 //   * Statistics are taken about the pivot bias_c + B_c * sum_k w[k,c] (the response to the constant part of u), which
 //     removes the large per-channel offset from the sums: the accumulators simply start at -B_c * sum_k w[k,c].
+//   * A block owns one 256-channel block and a CONTIGUOUS range of (sample, chunk) tiles: it stays inside one or two
+//     samples, so the per-sample affine is reloaded only at a sample switch and the halo frames of consecutive chunks
+//     hit L2.
+//
+// What was tried and measured on B200 (profiles/r2h): a thread-block-cluster form that also exchanged the GroupNorm
+// statistics through distributed shared memory and normalised its own rows in place out of L2 (one kernel for the whole
+// front half) cost 0.517 ms per velocity evaluation against 0.414 + 0.106 ms for this kernel + the streaming apply (the
+// conv is bound by the FMA pipe and the issue slots, so every phase that keeps its warps away from FFMA2 shows); a
+// dedicated producer warp (160 threads) capped the registers at 168 and spilled; global loads of the row statistics
+// were sunk by the compiler next to their use (barrier stalls 0.64 per issue) until they were moved to cp.async.
 //
 // 128 threads (thread = 2 channels x 32 frames); thread 0 issues one TMA tile copy per chunk two tiles ahead (62 frames
 // x 256 channels, out-of-range frames zero-filled), threads 0..61 prepare the per-row LayerNorm constants of the next
@@ -43,7 +47,7 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = ROWS * CB * 2;
 constexpr int RC_BYTES = 64 * 16;     // per stage: 64 rows x (rstd, rstd, -mean*rstd, -mean*rstd)
 constexpr int NTHREADS = 128;
-constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * RC_BYTES + 2 * 64 /*z flags*/ * 4 + 128 * 16 + CB * 8 + 64 + 2 * 64 * 16 * 4;
+constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * RC_BYTES + 64 + 2 * 64 * 16 * 4;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) {
@@ -65,25 +69,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                  : "memory");
   } while (!done);
 }
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_size() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
-  return v;
-}
 __device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) {
   return pack2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
@@ -95,12 +80,13 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
 }
 
 // one chunk: LayerNorm-modulate on load, 31-tap window, outputs.  MASKED: the tile touches frames outside [0, L)
+// One chunk: LayerNorm-modulate on load, 31-tap window, outputs.
+// MASKED: the tile touches frames outside [0, L) (first / last chunks of a sample): their u is forced to zero (the conv
+// is zero padded) and stores are predicated.  Interior tiles run the variant without any of that: measured 0.414 ms
+// per velocity against 0.486 ms for a single always-masked variant (B=26, L=1225; profiles/r2h).
 // CC: compile-time channel count (row stride of the outputs: the 64 stores of a tile then use immediate offsets from two
 // base registers, no pointer arithmetic on the issue slots), or 0 for a run-time C.
-// One code path for interior and boundary tiles (the unrolled body is ~34 KB of SASS; a second variant doubled the
-// instruction-cache misses): frames outside [0, L) carry rstd = 0, -mean*rstd = 0 in `rc`, and their u is forced to 0
-// (the conv is zero padded) by selecting a zero B term - two SEL on the ALU pipe, nothing on the FMA pipe.
-template <int CC, typename Mid>
+template <bool MASKED, int CC, typename Mid>
 __device__ __forceinline__ void conv_tile(const bf16* __restrict__ xs, const float4* __restrict__ rc,
                                           const f32x2 (&w2)[KW], f32x2 A2, f32x2 B2, f32x2 acc0, f32x2 ob2, int nvalid,
                                           int Crt, bf16* __restrict__ ub, bf16* __restrict__ gb, f32x2& S1, f32x2& S2,
@@ -116,11 +102,14 @@ __device__ __forceinline__ void conv_tile(const bf16* __restrict__ xs, const flo
     const f32x2 x2 = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(xs + r * CB));
     const float4 c4 = rc[r];  // (rstd, rstd, -mean*rstd, -mean*rstd): broadcast read, already packed
     const f32x2 rr = *reinterpret_cast<const f32x2*>(&c4.x), mm = *reinterpret_cast<const f32x2*>(&c4.z);
-    const bool inside = c4.x != 0.f;  // rstd > 0 for every frame of the sample
-    const f32x2 Bz = pack2(inside ? b0 : 0.f, inside ? b1 : 0.f);
+    f32x2 Bz = B2;
+    if (MASKED) {  // frames outside the sample carry rstd = -mean*rstd = 0: select a zero B term as well -> u = 0
+      const bool inside = c4.x != 0.f;
+      Bz = pack2(inside ? b0 : 0.f, inside ? b1 : 0.f);
+    }
     const f32x2 u2 = fma2(fma2(x2, rr, mm), A2, Bz);
     if (r >= PAD && r < PAD + TT) {  // centre rows: this tile owns them -> inner-residual operand of conv_3
-      if (r - PAD < nvalid) *reinterpret_cast<uint32_t*>(ub + (r - PAD) * C) = f32x2_to_bf16x2(u2);
+      if (!MASKED || r - PAD < nvalid) *reinterpret_cast<uint32_t*>(ub + (r - PAD) * C) = f32x2_to_bf16x2(u2);
     }
 #pragma unroll
     for (int j = 0; j < TT; ++j) {
@@ -131,7 +120,7 @@ __device__ __forceinline__ void conv_tile(const bf16* __restrict__ xs, const flo
   mid();  // the LayerNorm constants of the next tile: their inputs landed long ago, the output stores below hide them
 #pragma unroll
   for (int j = 0; j < TT; ++j) {
-    if (j < nvalid) {
+    if (!MASKED || j < nvalid) {
       S1 = add2(S1, acc[j]);
       S2 = fma2(acc[j], acc[j], S2);
       *reinterpret_cast<uint32_t*>(gb + j * C) = f32x2_to_bf16x2(add2(acc[j], ob2));
@@ -154,9 +143,9 @@ __device__ __forceinline__ void rc_prefetch(const DwFused& p, int b, int t, floa
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void rc_finish(const DwFused& p, int b, int t, const float* raw_row, float4* rc, float* zf) {
+__device__ __forceinline__ void rc_finish(const DwFused& p, int b, int t, const float* raw_row, float4* rc) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  float rstd = 0.f, nm = 0.f, z = 0.f;
+  float rstd = 0.f, nm = 0.f;
   if (t >= 0 && t < p.L) {
     float s = 0.f, qq = 0.f;
     if (p.parts <= 8) {
@@ -178,10 +167,8 @@ __device__ __forceinline__ void rc_finish(const DwFused& p, int b, int t, const 
     const float var = fmaxf(qq * inv_c - mean * mean, 0.f);
     rstd = rsqrtf(var + p.ln_eps);
     nm = -mean * rstd;
-    z = 1.f;
   }
-  *rc = make_float4(rstd, rstd, nm, nm);
-  *zf = z;
+  *rc = make_float4(rstd, rstd, nm, nm);  // frames outside the sample: zeros (conv_tile<MASKED> keys on rstd == 0)
 }
 __device__ __forceinline__ void tma_tile(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int t0, int b) {
   mbar_expect_tx(bar, TILE_BYTES);
@@ -220,81 +207,66 @@ __device__ __forceinline__ Affine make_affine(const DwFused& p, int b, int c) {
   return a;
 }
 
-// CLUSTER = true : a cluster of S CTAs owns one (sample, 256-channel block); GroupNorm statistics are exchanged through
-//                  distributed shared memory and every CTA normalises its own rows in place (one kernel).
-// CLUSTER = false: persistent blocks over contiguous (sample, chunk) tile ranges; per-chunk (mean, M2) partial statistics
-//                  out (layout (B, nchunk, C, 2)); merge + in-place streaming apply follow as separate launches.
-template <bool CLUSTER, int CC>
-__global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_gn_kernel(const __grid_constant__ CUtensorMap tmX, DwFused p,
-                                                                   float* __restrict__ part, int nchunk, int ncblk,
-                                                                   int ntiles) {
+// persistent blocks over contiguous (sample, chunk) tile ranges; per-chunk (mean, M2) partial statistics out (layout
+// (B, nchunk, C, 2), the layout launch_dw_merge consumes)
+template <int CC>
+__global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwFused p,
+                                                                float* __restrict__ part, int nchunk, int ncblk,
+                                                                int ntiles) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
-  float4* rcs = reinterpret_cast<float4*>(smem + STAGES * TILE_BYTES);   // [2][64]
-  float* zfs = reinterpret_cast<float*>(rcs + 2 * 64);                   // [2][64] (unused padding)
-  float4* cstat = reinterpret_cast<float4*>(zfs + 2 * 64);               // [128] (S1a, S1b, S2a, S2b) of this CTA
-  float2* scof = reinterpret_cast<float2*>(cstat + 128);                 // [256] (scale, offset) per channel
-  uint64_t* full = reinterpret_cast<uint64_t*>(scof + CB);               // [STAGES]
+  float4* rcs = reinterpret_cast<float4*>(smem + STAGES * TILE_BYTES);   // [2][64] LayerNorm constants per row
+  uint64_t* full = reinterpret_cast<uint64_t*>(rcs + 2 * 64);            // [STAGES]
   float* praw = reinterpret_cast<float*>(full + 8);                      // [2][64][RAW_FLOATS] staged row partials
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int cblk, t_lo, t_hi, unit_b = 0;
-  uint32_t rank = 0, S = 1;
-  if (CLUSTER) {
-    rank = cluster_rank(); S = cluster_size();
-    const int unit = blockIdx.x / S;
-    unit_b = unit / ncblk; cblk = unit % ncblk;
-    const int q = (nchunk + (int)S - 1) / (int)S;
-    t_lo = min((int)rank * q, nchunk); t_hi = min(t_lo + q, nchunk);  // chunk range of sample unit_b
-  } else {
-    cblk = blockIdx.x % ncblk;
-    const int slice = blockIdx.x / ncblk, nslices = gridDim.x / ncblk;
-    t_lo = (int)((int64_t)ntiles * slice / nslices); t_hi = (int)((int64_t)ntiles * (slice + 1) / nslices);
-  }
-  auto tile_b = [&](int tile) { return CLUSTER ? unit_b : tile / nchunk; };
-  auto tile_chunk = [&](int tile) { return CLUSTER ? tile : tile % nchunk; };
+  const int tid = threadIdx.x;
+  const int cblk = blockIdx.x % ncblk;
+  const int slice = blockIdx.x / ncblk, nslices = gridDim.x / ncblk;
+  const int t_lo = (int)((int64_t)ntiles * slice / nslices), t_hi = (int)((int64_t)ntiles * (slice + 1) / nslices);
+  if (t_lo >= t_hi) return;
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();  // h and its row statistics come from the previous kernel
   if (tid == 0) {
     for (int d = 0; d < STAGES - 1; ++d)
       if (t_lo + d < t_hi)
-        tma_tile(&tmX, &full[d], ring + d * TILE_BYTES, cblk * CB, tile_chunk(t_lo + d) * TT - PAD, tile_b(t_lo + d));
+        tma_tile(&tmX, &full[d], ring + d * TILE_BYTES, cblk * CB, ((t_lo + d) % nchunk) * TT - PAD, (t_lo + d) / nchunk);
   }
   const int c = cblk * CB + tid * 2;
   f32x2 w2[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) w2[k] = *reinterpret_cast<const f32x2*>(p.w + (int64_t)k * p.C + c);
-  if (t_lo < t_hi && tid < ROWS) {  // LayerNorm constants of the first tile (latency exposed once per block)
-    const int t = tile_chunk(t_lo) * TT - PAD + tid;
-    rc_prefetch(p, tile_b(t_lo), t, praw + tid * RAW_FLOATS);
-    rc_finish(p, tile_b(t_lo), t, praw + tid * RAW_FLOATS, &rcs[tid], &zfs[tid]);
+  if (tid < ROWS) {  // LayerNorm constants of the first tile (latency exposed once per block)
+    const int t = (t_lo % nchunk) * TT - PAD + tid;
+    rc_prefetch(p, t_lo / nchunk, t, praw + tid * RAW_FLOATS);
+    rc_finish(p, t_lo / nchunk, t, praw + tid * RAW_FLOATS, &rcs[tid]);
   }
   __syncthreads();
-  Affine af = make_affine(p, tile_b(t_lo < t_hi ? t_lo : 0), c);
-  int cur_b = tile_b(t_lo < t_hi ? t_lo : 0);
-  f32x2 S1 = 0ull, S2 = 0ull;
+  int cur_b = t_lo / nchunk;
+  Affine af = make_affine(p, cur_b, c);
   int slot = 0;
   uint32_t phase = 0;
   for (int tile = t_lo; tile < t_hi; ++tile) {
-    const int b = tile_b(tile), chunk = tile_chunk(tile);
+    const int b = tile / nchunk, chunk = tile % nchunk;
     const int it = tile - t_lo;
     if (tid == 0) {  // refill the slot drained in the previous iteration (all threads passed its __syncthreads)
       const int nxt = tile + STAGES - 1;
       if (nxt < t_hi) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const int ns = (slot + STAGES - 1) % STAGES;
-        tma_tile(&tmX, &full[ns], ring + ns * TILE_BYTES, cblk * CB, tile_chunk(nxt) * TT - PAD, tile_b(nxt));
+        tma_tile(&tmX, &full[ns], ring + ns * TILE_BYTES, cblk * CB, (nxt % nchunk) * TT - PAD, nxt / nchunk);
       }
     }
     const bool have_next = tile + 1 < t_hi;
-    const int nb = have_next ? tile_b(tile + 1) : 0, nt = have_next ? tile_chunk(tile + 1) * TT - PAD + tid : -1;
+    const int nb = have_next ? (tile + 1) / nchunk : 0, nt = have_next ? ((tile + 1) % nchunk) * TT - PAD + tid : -1;
     float* raw_next = praw + (((it + 1) & 1) * 64 + tid) * RAW_FLOATS;
     if (have_next && tid < ROWS) rc_prefetch(p, nb, nt, raw_next);
-    if (!CLUSTER && b != cur_b) {  // sample switch (warp-uniform, once or twice per block)
+    if (b != cur_b) {  // sample switch (warp-uniform, once or twice per block)
       cur_b = b;
       af = make_affine(p, b, c);
     }
@@ -305,14 +277,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_gn_kernel(const __grid_
     bf16* gb = p.g + ((int64_t)b * p.L + t0) * p.C + c;
     f32x2 T1 = 0ull, T2 = 0ull;
     const float4* rc = rcs + (it & 1) * 64;
-    conv_tile<CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, min(TT, p.L - t0), p.C, ub, gb, T1, T2, [&]() {
-      if (have_next && tid < ROWS)
-        rc_finish(p, nb, nt, raw_next, &rcs[((it + 1) & 1) * 64 + tid], &zfs[((it + 1) & 1) * 64 + tid]);
-    });
-    if (CLUSTER) {
-      S1 = add2(S1, T1);
-      S2 = add2(S2, T2);
-    } else {  // per-chunk (mean, M2) about the pivot: mean = pivot + S/n, M2 = Q - S^2/n
+    auto mid = [&]() {
+      if (have_next && tid < ROWS) rc_finish(p, nb, nt, raw_next, &rcs[((it + 1) & 1) * 64 + tid]);
+    };
+    const bool interior = (t0 - PAD >= 0) && (t0 + TT + PAD <= p.L);
+    if (interior) conv_tile<false, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, TT, p.C, ub, gb, T1, T2, mid);
+    else conv_tile<true, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, min(TT, p.L - t0), p.C, ub, gb, T1, T2, mid);
+    {  // per-chunk (mean, M2) about the pivot: mean = pivot + S/n, M2 = Q - S^2/n
       float s0, s1, q0, q1;
       unpack2(T1, s0, s1);
       unpack2(T2, q0, q1);
@@ -324,70 +295,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_gn_kernel(const __grid_
     __syncthreads();  // the tile slot and the other constants buffer may be overwritten from here on
     if (++slot == STAGES) { slot = 0; phase ^= 1; }
   }
-  if (!CLUSTER) return;
-
-  // ===================== GroupNorm statistics across the cluster (deterministic order) =====================
-  {
-    float s0, s1, q0, q1;
-    unpack2(S1, s0, s1);
-    unpack2(S2, q0, q1);
-    cstat[tid] = make_float4(s0, s1, q0, q1);
-  }
-  cluster_arrive();
-  cluster_wait();
-  {
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    const uint32_t local = s32(&cstat[tid]);
-    for (uint32_t r = 0; r < S; ++r) {
-      const float4 v = ld_dsmem_f4(local, r);
-      s0 += v.x; s1 += v.y; q0 += v.z; q1 += v.w;
-    }
-    const float inv_n = 1.0f / (float)p.L;
-    const float d0 = s0 * inv_n, d1 = s1 * inv_n;  // mean - pivot
-    const float v0 = fmaxf(q0 * inv_n - d0 * d0, 0.f), v1 = fmaxf(q1 * inv_n - d1 * d1, 0.f);
-    const float2 ga = *reinterpret_cast<const float2*>(p.gamma + c), be = *reinterpret_cast<const float2*>(p.beta + c);
-    const float sc0 = ga.x * rsqrtf(v0 + p.gn_eps), sc1 = ga.y * rsqrtf(v1 + p.gn_eps);
-    scof[tid * 2] = make_float2(sc0, be.x - (af.piv0 + d0) * sc0);
-    scof[tid * 2 + 1] = make_float2(sc1, be.y - (af.piv1 + d1) * sc1);
-  }
-  cluster_arrive();  // peers may retire once every CTA has read their statistics (waited on at the very end)
-  __syncthreads();
-
-  // ===================== normalise this CTA's own rows in place (they are still in L2) =====================
-  {
-    const int cg = lane * 8;  // 8 channels = 16 bytes; a warp covers one 256-channel row segment
-    f32x2 sc2[4], of2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 e0 = scof[cg + 2 * j], e1 = scof[cg + 2 * j + 1];
-      sc2[j] = pack2(e0.x, e1.x);
-      of2[j] = pack2(e0.y, e1.y);
-    }
-    const int r_lo = t_lo * TT, r_hi = min(t_hi * TT, p.L);
-    bf16* base = p.g + ((int64_t)unit_b * p.L) * p.C + cblk * CB + cg;
-    constexpr int U = 8;
-    int r = r_lo + warp;
-    for (; r + 4 * (U - 1) < r_hi; r += 4 * U) {
-      uint4 v[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) v[k] = __ldcg(reinterpret_cast<const uint4*>(base + (int64_t)(r + 4 * k) * p.C));
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        uint32_t* w = reinterpret_cast<uint32_t*>(&v[k]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = f32x2_to_bf16x2(fma2(bf16x2_to_f32x2(w[j]), sc2[j], of2[j]));
-        *reinterpret_cast<uint4*>(base + (int64_t)(r + 4 * k) * p.C) = v[k];
-      }
-    }
-    for (; r < r_hi; r += 4) {
-      uint4 v = __ldcg(reinterpret_cast<const uint4*>(base + (int64_t)r * p.C));
-      uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = f32x2_to_bf16x2(fma2(bf16x2_to_f32x2(w[j]), sc2[j], of2[j]));
-      *reinterpret_cast<uint4*>(base + (int64_t)r * p.C) = v;
-    }
-  }
-  cluster_wait();
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -397,62 +304,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 void dwconv_fused_init() {
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_gn_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_gn_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_gn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_gn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
 }
 
 bool dwconv_fused_supported(const DwFused& p) {
   return p.C % CB == 0 && p.rowstat != nullptr && p.parts >= 2 && p.parts % 2 == 0 && p.tma_encode != nullptr &&
-         (reinterpret_cast<uintptr_t>(p.h) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.g) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(p.h) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.g) & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(p.u) & 3) == 0;
-}
-
-// cluster size: the S in {1,2,4,8} that minimises (waves of CTAs) x (chunks per CTA + fixed per-CTA cost)
-int dwconv_fused_cluster(int B, int L, int C, int num_sms) {
-  const int units = B * (C / CB), nchunk = dw_nchunk(L), slots = 2 * num_sms;
-  int best = 1;
-  long best_cost = -1;
-  for (int S = 1; S <= 8; S *= 2) {
-    if (S > 1 && (nchunk + S - 1) / S < 2) break;
-    const long waves = ((long)units * S + slots - 1) / slots;
-    const long cost = waves * ((nchunk + S - 1) / S + 2);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = S; }
-  }
-  return best;
-}
-
-void launch_dwconv_fused(const DwFused& p, int num_sms, cudaStream_t stream) {
-  FLM_REQUIRE(dwconv_fused_supported(p), "dwconv_fused: unsupported problem");
-  if (p.B == 0 || p.L == 0) return;
-  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(p.tma_encode);
-  CUtensorMap tm;
-  cuuint64_t dims[3] = {(cuuint64_t)p.C, (cuuint64_t)p.L, (cuuint64_t)p.B};
-  cuuint64_t strides[2] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.C * 2 * (cuuint64_t)p.L};
-  cuuint32_t box[3] = {CB, (cuuint32_t)ROWS, 1}, estr[3] = {1, 1, 1};
-  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(p.h), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(dwconv_fused h) failed: " + std::to_string((int)r));
-  const int ncblk = p.C / CB, nchunk = dw_nchunk(p.L);
-  const int S = dwconv_fused_cluster(p.B, p.L, p.C, num_sms);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(p.B * ncblk * S));
-  cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (p.C == 1024) FLM_CUDA(cudaLaunchKernelEx(&cfg, dwconv_ln_gn_kernel<true, 1024>, tm, p, (float*)nullptr, nchunk, ncblk, 0));
-  else FLM_CUDA(cudaLaunchKernelEx(&cfg, dwconv_ln_gn_kernel<true, 0>, tm, p, (float*)nullptr, nchunk, ncblk, 0));
-  FLM_LAUNCH_CHECK();
 }
 
 // LayerNorm-on-load + depthwise conv, persistent; writes u, the un-normalised d (into p.g) and the per-chunk partial
@@ -475,9 +334,11 @@ void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t s
   if (slices > ntiles) slices = ntiles;
   if (slices < 1) slices = 1;
   if (p.C == 1024)
-    dwconv_ln_gn_kernel<false, 1024><<<slices * ncblk, NTHREADS, SMEM_BYTES, stream>>>(tm, p, part, nchunk, ncblk, ntiles);
+    launch_pdl(dwconv_ln_kernel<1024>, dim3(slices * ncblk), dim3(NTHREADS), (size_t)SMEM_BYTES, stream, tm, p, part, nchunk, ncblk,
+               ntiles);
   else
-    dwconv_ln_gn_kernel<false, 0><<<slices * ncblk, NTHREADS, SMEM_BYTES, stream>>>(tm, p, part, nchunk, ncblk, ntiles);
+    launch_pdl(dwconv_ln_kernel<0>, dim3(slices * ncblk), dim3(NTHREADS), (size_t)SMEM_BYTES, stream, tm, p, part, nchunk, ncblk,
+               ntiles);
   FLM_LAUNCH_CHECK();
 }
 

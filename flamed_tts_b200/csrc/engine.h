@@ -35,7 +35,6 @@ struct flm_ctx {
   int device = 0;
   int num_sms = 0;
   void* tma_encode = nullptr;  // cuTensorMapEncodeTiled
-  int gemm_gen = 2;            // 2: CTA-pair kernel (tapgemm_tc2.cu) where it applies; 1: first-generation kernel only
   // profiler state
   bool prof_on = false;
   struct Rec { int kc; cudaEvent_t a, b; double flops, bytes; std::string tag; };
@@ -239,7 +238,7 @@ struct Engine {
     if (a_bf16) {
       if (!l.w16) throw Error(FLM_ERR_ARG, "layer has no bf16 weights");
       p.W = l.w16;
-      if (ctx->gemm_gen >= 2 && tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, s);
+      if (tapgemm_tc2_supported(p)) launch_tapgemm_tc2(p, ctx->tma_encode, ctx->num_sms, s);
       else launch_tapgemm_tc(p, ctx->tma_encode, ctx->num_sms, s);
     } else {
       p.W = l.w32;

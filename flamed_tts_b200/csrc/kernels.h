@@ -36,7 +36,8 @@ struct LnMod {
 };
 void launch_ln_mod(const LnMod& p, cudaStream_t stream);
 
-// ---- depthwise conv k<=31 over time (channels-last) + per-(b,chunk,c) partial statistics
+// ---- depthwise conv k=31 over time (channels-last) + per-(b,chunk,c) partial statistics: fp32 parity mode (the bf16
+//      mode runs the LayerNorm-fused kernel of dwconv_fused.cu); also the parameter block of launch_dw_merge
 struct DwConv {
   const void* x; void* y; int io_bf16;  // (B,L,C)
   const float* w;   // (KW, C) tap-major
@@ -48,24 +49,19 @@ struct DwConv {
   const float* gamma; const float* beta; float eps;
   float* scale; float* offset;
   int* counters;    // (B, C/256) arrival tickets, zero before the first launch, re-armed by the kernel
-  void* tma_encode; // cuTensorMapEncodeTiled entry point: non-null selects the persistent TMA-pipelined kernel (bf16)
 };
 constexpr int DW_TT = 32;
 inline int dw_nchunk(int L) { return (L + DW_TT - 1) / DW_TT; }
 void launch_dwconv(const DwConv& p, cudaStream_t stream);
-// tensor-core form (dwconv_tc.cu: bf16, k=31, C % 64 == 0): writes y and the chunk partials only; follow with
-// launch_dw_merge to turn the partials into the GroupNorm(C,C) scale / offset
-void launch_dwconv_tc(const DwConv& p, int num_sms, cudaStream_t stream);
-bool dwconv_tc_supported(const DwConv& p);
-void dwconv_tc_init();
+// merge of the per-chunk partials (B, nchunk, C, 2) into the GroupNorm(C,C) scale / offset (bf16 mode, after launch_dwconv_ln)
 void launch_dw_merge(const DwConv& p, cudaStream_t stream);
 
-// ---- ConvNeXt front half in one kernel (dwconv_fused.cu, bf16 mode with a bf16 residual stream):
-//      u = LN(h)*(1+scale)+shift, d = dwconv31(u)+bias, g = GroupNorm(C,C)(d) over the whole time axis
+// ---- LayerNorm + modulate fused into the depthwise conv (dwconv_fused.cu, bf16 mode with a bf16 residual stream):
+//      u = LN(h)*(1+scale)+shift, d = dwconv31(u)+bias (+ per-chunk statistics of d for the GroupNorm that follows)
 struct DwFused {
   const bf16* h;  // (B,L,C) residual stream = LayerNorm input
   bf16* u;        // (B,L,C) out: modulated LayerNorm output (inner residual of the ConvNeXt block)
-  bf16* g;        // (B,L,C) out: normalised depthwise-conv output (input of conv_2)
+  bf16* g;        // (B,L,C) out: depthwise-conv output d (normalised in place afterwards: input of conv_2)
   const float* rowstat; int parts;  // (B*L, parts) float2 (sum, sumsq) partials of the rows of h (TapGemm::rowstat)
   const float* ln_w; const float* ln_b;  // LayerNorm affine (nullable: FinalLayer's LN has none)
   const float* shift; const float* scale; int64_t mod_bstride;  // adaLN modulation of sample b (nullable)
@@ -77,10 +73,8 @@ struct DwFused {
   int B, L, C;
   void* tma_encode;
 };
-void launch_dwconv_fused(const DwFused& p, int num_sms, cudaStream_t stream);
 void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t stream);
 bool dwconv_fused_supported(const DwFused& p);
-int dwconv_fused_cluster(int B, int L, int C, int num_sms);
 void dwconv_fused_init();
 
 // ---- generic grouped statistics over (rows x channels-in-group) for GroupNorm(G) in the cond
@@ -94,10 +88,6 @@ void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, f
 void launch_gn_finalize(const float* part, int B, int L, int C, int G, int nchunk, int chunk_rows,
                         const float* gamma, const float* beta, float eps, float* scale, float* offset,
                         cudaStream_t stream);
-
-// ---- ConvNeXt GroupNorm(C,C): merge of the depthwise kernel's partials fused with the affine apply
-void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, const float* gamma, const float* beta,
-                        float eps, int B, int L, int C, int nchunk, int chunk_rows, cudaStream_t stream);
 
 // ---- y = x*scale[b,c] + offset[b,c], streaming (ConvNeXt GroupNorm apply after the fused finalisation)
 void launch_gn_stream(const void* x, void* y, int io_bf16, const float* scale, const float* offset, int B, int L, int C,

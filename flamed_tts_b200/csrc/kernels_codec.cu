@@ -99,6 +99,8 @@ __device__ __forceinline__ f32x2 ld_pair2(const T* p) {
 // thread travel as packed fp32x2 (FFMA2).
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
+  pdl_trigger();
+  pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   const int n0 = (blockIdx.y * blockDim.y + threadIdx.y) * ACT_TT;
   const int b = blockIdx.z;
@@ -286,11 +288,11 @@ void launch_act1d(const Act1d& p, cudaStream_t stream) {
   dim3 grid((p.C / 2) / bx, (p.T + by * ACT_TT - 1) / (by * ACT_TT), p.B);
   FLM_REQUIRE(grid.y <= 65535, "act1d: sequence too long");
   if (p.io_bf16) {
-    if (p.fast_sin) act1d_kernel<bf16, true><<<grid, block, 0, stream>>>(p);
-    else act1d_kernel<bf16, false><<<grid, block, 0, stream>>>(p);
+    if (p.fast_sin) launch_pdl(act1d_kernel<bf16, true>, grid, block, (size_t)0, stream, p);
+    else launch_pdl(act1d_kernel<bf16, false>, grid, block, (size_t)0, stream, p);
   } else {
-    if (p.fast_sin) act1d_kernel<float, true><<<grid, block, 0, stream>>>(p);
-    else act1d_kernel<float, false><<<grid, block, 0, stream>>>(p);
+    if (p.fast_sin) launch_pdl(act1d_kernel<float, true>, grid, block, (size_t)0, stream, p);
+    else launch_pdl(act1d_kernel<float, false>, grid, block, (size_t)0, stream, p);
   }
   FLM_LAUNCH_CHECK();
 }

@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_kernel(LnMod p, int64
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  pdl_trigger();
+  pdl_wait();
   auto issue = [&](int64_t r, int slot) {  // lane 0 only
     const uint32_t bar = ln_smem_u32(&bars[slot]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * sizeof(TI)))
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, 1) ln_mod_bf16_kernel(LnMod p, 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  pdl_trigger();
+  pdl_wait();
   auto issue = [&](int64_t r, int slot) {  // lane 0 only
     const uint32_t bar = ln_smem_u32(&bars[slot]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(C * 2)) : "memory");
@@ -296,13 +300,13 @@ void ln_launch(const LnMod& p, int sms, cudaStream_t stream) {
   if (blocks > sms) blocks = sms;
   const int64_t total_warps = blocks * LN_WARPS;
   const int64_t rpw = (p.rows + total_warps - 1) / total_warps;
-  if (p.x_bf16 && p.y_bf16 && !p.relu_in && NV % 2 == 0 && p.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
-      !getenv("FLAMED_B200_LN_V1"))
-    ln_mod_bf16_kernel<(NV >= 2 ? NV / 2 : 1)><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, bf16>(), stream>>>(p, rpw);
+  if (p.x_bf16 && p.y_bf16 && !p.relu_in && NV % 2 == 0 && p.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0)
+    launch_pdl(ln_mod_bf16_kernel<(NV >= 2 ? NV / 2 : 1)>, dim3((unsigned)blocks), dim3(LN_WARPS * 32),
+               (size_t)ln_smem_bytes<NV, bf16>(), stream, p, rpw);
   else if (p.x_bf16)
-    ln_mod_kernel<NV, bf16><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, bf16>(), stream>>>(p, rpw);
+    launch_pdl(ln_mod_kernel<NV, bf16>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), (size_t)ln_smem_bytes<NV, bf16>(), stream, p, rpw);
   else
-    ln_mod_kernel<NV, float><<<(unsigned)blocks, LN_WARPS * 32, ln_smem_bytes<NV, float>(), stream>>>(p, rpw);
+    launch_pdl(ln_mod_kernel<NV, float>, dim3((unsigned)blocks), dim3(LN_WARPS * 32), (size_t)ln_smem_bytes<NV, float>(), stream, p, rpw);
 }
 
 }  // namespace
@@ -501,144 +505,13 @@ __global__ void __launch_bounds__(128) dwconv_kernel(DwConv p) {
   dw_finalize(p, b, blockIdx.x, chunk, gridDim.y, gridDim.x, c);
 }
 
-// Persistent, TMA-pipelined form of the same computation for bf16 storage (the throughput mode): one block
-// streams (sample, chunk) tiles of a FIXED 256-channel block through a DWP_STAGES-deep shared-memory ring.
-// Each tile is one 3-D bulk tensor copy (256 channels x 62 frames, out-of-range frames zero-filled by the TMA
-// unit = the conv's zero padding), issued DWP_STAGES-1 tiles ahead by thread 0, so ~2-3 tiles (60-90 KB) per
-// block are in flight while the 31-tap FFMA2 window runs; the tap weights stay in registers for the whole
-// kernel because the grid is a multiple of the number of channel blocks.
-template <int KW, int DWP_STAGES>
-__global__ void __launch_bounds__(128) dwconv_tma_kernel(const __grid_constant__ CUtensorMap tmX, DwConv p, int nchunk,
-                                                         int ncblk, int ntiles) {
-  constexpr int PAD = KW / 2;
-  constexpr int ROWS = DW_TT + KW - 1;
-  constexpr int TILE_BYTES = ROWS * 256 * 2;
-  extern __shared__ __align__(128) uint8_t dwp_smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dwp_smem + DWP_STAGES * TILE_BYTES);
-  const int cblk = blockIdx.x % ncblk;  // gridDim.x % ncblk == 0: constant for every tile of this block
-  const int c = cblk * 256 + threadIdx.x * 2;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < DWP_STAGES; ++i)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ln_smem_u32(&bars[i])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // work item w of this block: tile id (b * nchunk + chunk) = blockIdx.x / ncblk + w * (gridDim.x / ncblk)
-  const int tstride = gridDim.x / ncblk;
-  const int tfirst = blockIdx.x / ncblk;
-  auto issue = [&](int tile, int slot) {  // thread 0 only
-    const int b = tile / nchunk, chunk = tile % nchunk;
-    const uint32_t bar = ln_smem_u32(&bars[slot]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TILE_BYTES) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-            "r"(ln_smem_u32(dwp_smem + slot * TILE_BYTES)),
-        "l"(reinterpret_cast<uint64_t>(&tmX)), "r"(bar), "r"(cblk * 256), "r"(chunk * DW_TT - PAD), "r"(b)
-        : "memory");
-  };
-  if (threadIdx.x == 0) {
-    for (int d = 0; d < DWP_STAGES - 1; ++d)
-      if (tfirst + d * tstride < ntiles) issue(tfirst + d * tstride, d);
-  }
-  f32x2 w2[KW];
-#pragma unroll
-  for (int k = 0; k < KW; ++k) w2[k] = *reinterpret_cast<const f32x2*>(p.w + (int64_t)k * p.C + c);
-  const f32x2 bias2 = *reinterpret_cast<const f32x2*>(p.bias + c);
-  int slot = 0;
-  uint32_t phase = 0;
-  for (int tile = tfirst; tile < ntiles; tile += tstride) {
-    // refill the slot that was drained in the previous iteration (all threads passed its __syncthreads)
-    if (threadIdx.x == 0) {
-      const int nxt = tile + (DWP_STAGES - 1) * tstride;
-      if (nxt < ntiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(nxt, (slot + DWP_STAGES - 1) % DWP_STAGES);
-      }
-    }
-    {
-      const uint32_t bar = ln_smem_u32(&bars[slot]);
-      uint32_t done;
-      do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(phase)
-            : "memory");
-      } while (!done);
-    }
-    const bf16* xs = reinterpret_cast<const bf16*>(dwp_smem + slot * TILE_BYTES) + threadIdx.x * 2;
-    f32x2 acc[DW_TT];
-#pragma unroll
-    for (int j = 0; j < DW_TT; ++j) acc[j] = 0ull;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      const f32x2 x2 = lds_pair<bf16>(xs + r * 256);
-#pragma unroll
-      for (int j = 0; j < DW_TT; ++j) {
-        const int tap = r - j;  // compile-time after unrolling
-        if (tap >= 0 && tap < KW) acc[j] = fma2(w2[tap], x2, acc[j]);
-      }
-    }
-    __syncthreads();  // the slot may be overwritten from here on
-    const int b = tile / nchunk, chunk = tile % nchunk;
-    const int t0 = chunk * DW_TT;
-    const int nvalid = min(DW_TT, p.L - t0);
-    bf16* yb = static_cast<bf16*>(p.y) + ((int64_t)b * p.L + t0) * p.C + c;
-    f32x2 s2 = 0ull;
-    // statistics about the pivot bias[c] (acc holds y - bias): S = sum acc, Q = sum acc^2 -> mean = bias + S/n,
-    // M2 = Q - S^2/n; the bias is added on the way out
-    f32x2 q2 = 0ull;
-    if (nvalid == DW_TT) {  // full chunk: no predicates, running pointer
-#pragma unroll
-      for (int j = 0; j < DW_TT; ++j) {
-        s2 = add2(s2, acc[j]);
-        q2 = fma2(acc[j], acc[j], q2);
-        float a0, a1;
-        unpack2(add2(acc[j], bias2), a0, a1);
-        st2<bf16>(yb, a0, a1);
-        yb += p.C;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < DW_TT; ++j) {
-        if (j < nvalid) {
-          s2 = add2(s2, acc[j]);
-          q2 = fma2(acc[j], acc[j], q2);
-          float a0, a1;
-          unpack2(add2(acc[j], bias2), a0, a1);
-          st2<bf16>(yb + (int64_t)j * p.C, a0, a1);
-        }
-      }
-    }
-    float s0, s1, q0, q1, b0, b1;
-    unpack2(s2, s0, s1);
-    unpack2(q2, q0, q1);
-    unpack2(bias2, b0, b1);
-    const float inv = 1.0f / (float)nvalid;
-    const float d0 = s0 * inv, d1 = s1 * inv;
-    const float m0 = b0 + d0, m1 = b1 + d1;
-    q0 = fmaxf(q0 - s0 * d0, 0.f);
-    q1 = fmaxf(q1 - s1 * d1, 0.f);
-    float* part = p.part + (((int64_t)b * nchunk + chunk) * p.C + c) * 2;
-    *reinterpret_cast<float4*>(part) = make_float4(m0, q0, m1, q1);
-    if (++slot == DWP_STAGES) { slot = 0; phase ^= 1; }
-  }
-}
-
-// statistics merge after the persistent kernel (a per-tile ticket + __threadfence there would stall every tile on
-// its own stores): thread = 2 channels of one sample
-__global__ void __launch_bounds__(128) dw_merge_kernel(DwConv p, int nchunk) {
-  const int idx = blockIdx.x * 128 + threadIdx.x;  // over B * C/2
-  const int half_c = p.C >> 1;
-  if (idx >= p.B * half_c) return;
-  dw_merge(p, idx / half_c, nchunk, (idx % half_c) * 2);
-}
-
 // bf16-mode form: one warp per (sample, 64 channels); lane = 2 channels, the chunks are split over the 4 warps of
 // a block and combined through shared memory in a fixed order (deterministic); fp32 with the chunk means taken
 // relative to the first chunk's mean, which keeps the second moment free of cancellation at bf16-level accuracy
 __global__ void __launch_bounds__(128) dw_merge_fast_kernel(DwConv p, int nchunk) {
   __shared__ float red[4][32][4];
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cgroups = p.C >> 6;
   const int b = blockIdx.x / cgroups, c = (blockIdx.x % cgroups) * 64 + lane * 2;
@@ -679,6 +552,8 @@ __global__ void __launch_bounds__(256) gn_stream_kernel(const T* __restrict__ x,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ offset, int L, int C) {
   constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte vector
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * GNS_ROWS;
   const int nrows = min(GNS_ROWS, L - r0);
@@ -748,53 +623,16 @@ __global__ void __launch_bounds__(256) gn_stream_kernel(const T* __restrict__ x,
 
 }  // namespace
 
+// fp32 parity mode: the depthwise conv of the ConvNeXt block with the GroupNorm statistics finalised by the last block
+// of each (sample, channel block).  The bf16 mode uses dwconv_fused.cu (LayerNorm fused in) + launch_dw_merge.
 void launch_dwconv(const DwConv& p, cudaStream_t stream) {
   FLM_REQUIRE(p.KW == 31, "dwconv: only kernel_size 31 is compiled (configs/prob.yaml convnext.kernel_size)");
   FLM_REQUIRE(p.C % 256 == 0, "dwconv: C must be a multiple of 256");
+  FLM_REQUIRE(!p.io_bf16, "dwconv: the bf16 mode runs the LayerNorm-fused kernel (launch_dwconv_ln)");
   if (p.B == 0 || p.L == 0) return;
   constexpr int ROWS = DW_TT + 31 - 1;
-  if (p.io_bf16 && p.tma_encode && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) {
-    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(p.tma_encode);
-    CUtensorMap tm;
-    cuuint64_t dims[3] = {(cuuint64_t)p.C, (cuuint64_t)p.L, (cuuint64_t)p.B};
-    cuuint64_t strides[2] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.C * 2 * (cuuint64_t)p.L};
-    cuuint32_t box[3] = {256, (cuuint32_t)ROWS, 1}, estr[3] = {1, 1, 1};
-    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.x), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) throw Error(-2, "cuTensorMapEncodeTiled(dwconv x) failed: " + std::to_string((int)r));
-    const int nchunk = dw_nchunk(p.L), ncblk = p.C / 256;
-    const int ntiles = p.B * nchunk;  // (sample, chunk) tiles per channel block
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    // 3-deep ring with two resident blocks per SM by default; FLAMED_B200_DWCONV_RING=2 selects a 2-deep ring with
-    // three blocks per SM (12 warps) - measured equal (5.0 vs 5.1 ms per 40 launches at 79k frames): the kernel is
-    // FMA-pipe bound, not latency bound
-    static const bool ring3 = [] { const char* e = getenv("FLAMED_B200_DWCONV_RING"); return !(e && atoi(e) == 2); }();
-    const int ctas_per_sm = ring3 ? 2 : 3;
-    int per_cblk = (ctas_per_sm * sms) / ncblk;
-    if (per_cblk > ntiles) per_cblk = ntiles;
-    if (per_cblk < 1) per_cblk = 1;
-    if (ring3)
-      dwconv_tma_kernel<31, 3><<<per_cblk * ncblk, 128, 3 * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
-    else
-      dwconv_tma_kernel<31, 2><<<per_cblk * ncblk, 128, 2 * ROWS * 256 * 2 + 64, stream>>>(tm, p, nchunk, ncblk, ntiles);
-    FLM_LAUNCH_CHECK();
-    launch_dw_merge(p, stream);
-    return;
-  }
   dim3 grid(p.C / 256, dw_nchunk(p.L), p.B);
-  if (p.io_bf16)
-    dwconv_kernel<bf16, 31><<<grid, 128, ROWS * 256 * 2, stream>>>(p);
-  else
-    dwconv_kernel<float, 31><<<grid, 128, ROWS * 256 * 4, stream>>>(p);
+  dwconv_kernel<float, 31><<<grid, 128, ROWS * 256 * 4, stream>>>(p);
   FLM_LAUNCH_CHECK();
 }
 
@@ -897,87 +735,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApply p) {
   st4<TY>(static_cast<TY*>(p.y) + row * p.C + c, v);
 }
 
-// GroupNorm(C,C) of the ConvNeXt block, statistics merge fused in: block = (32 rows, sample b), thread = 4
-// channels.  Prologue: Chan-merge (fp64) of the per-chunk (mean, M2) partials the depthwise kernel wrote
-// -> scale = gamma*rstd, offset = beta - mean*scale in registers; body: y = x*scale + offset, 8 B/16 B vectors.
-constexpr int GNF_ROWS = 128;
-template <typename T>
-__global__ void __launch_bounds__(256) gn_convnext_kernel(const T* __restrict__ x, T* __restrict__ y,
-                                                          const float* __restrict__ part, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float eps, int L, int C,
-                                                          int nchunk, int chunk_rows) {
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * GNF_ROWS;
-  const int nrows = min(GNF_ROWS, L - r0);
-  for (int c = threadIdx.x * 4; c < C; c += 256 * 4) {
-    // two passes over the partials, no divisions: mean = sum(n_k m_k)/N; M2 = sum(q_k + n_k (m_k - mean)^2)
-    const float* pbase = part + ((int64_t)b * nchunk * C + c) * 2;
-    double sm[4] = {0, 0, 0, 0};
-    for (int k = 0; k < nchunk; ++k) {
-      const float* pp = pbase + (int64_t)k * C * 2;
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pp));
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pp + 4));
-      const double nb = (double)min(chunk_rows, L - k * chunk_rows);
-      sm[0] += nb * p0.x; sm[1] += nb * p0.z; sm[2] += nb * p1.x; sm[3] += nb * p1.z;
-    }
-    const double inv_n = 1.0 / (double)L;
-    double mean[4], m2[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) mean[j] = sm[j] * inv_n;
-    for (int k = 0; k < nchunk; ++k) {
-      const float* pp = pbase + (int64_t)k * C * 2;
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pp));
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pp + 4));
-      const double nb = (double)min(chunk_rows, L - k * chunk_rows);
-      const double d0 = p0.x - mean[0], d1 = p0.z - mean[1], d2 = p1.x - mean[2], d3 = p1.z - mean[3];
-      m2[0] += p0.y + nb * d0 * d0; m2[1] += p0.w + nb * d1 * d1;
-      m2[2] += p1.y + nb * d2 * d2; m2[3] += p1.w + nb * d3 * d3;
-    }
-    float ga[4], be[4], sc[4], of[4];
-    ld4<float>(gamma + c, ga);
-    ld4<float>(beta + c, be);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float rstd = rsqrtf((float)(m2[j] * inv_n) + eps);
-      sc[j] = ga[j] * rstd;
-      of[j] = be[j] - (float)mean[j] * sc[j];
-    }
-    const T* xp = x + ((int64_t)b * L + r0) * C + c;
-    T* yp = y + ((int64_t)b * L + r0) * C + c;
-#pragma unroll 8
-    for (int r = 0; r < nrows; ++r) {
-      float v[4];
-      ld4<T>(xp + (int64_t)r * C, v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = fmaf(v[j], sc[j], of[j]);
-      st4<T>(yp + (int64_t)r * C, v);
-    }
-  }
-}
-
 }  // namespace
-
-void launch_gn_convnext(const void* x, void* y, int io_bf16, const float* part, const float* gamma, const float* beta,
-                        float eps, int B, int L, int C, int nchunk, int chunk_rows, cudaStream_t stream) {
-  FLM_REQUIRE(C % 4 == 0, "gn_convnext: C % 4 != 0");
-  if (B == 0 || L == 0) return;
-  dim3 grid((L + GNF_ROWS - 1) / GNF_ROWS, B);
-  if (io_bf16)
-    gn_convnext_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), part, gamma,
-                                                       beta, eps, L, C, nchunk, chunk_rows);
-  else
-    gn_convnext_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), part,
-                                                        gamma, beta, eps, L, C, nchunk, chunk_rows);
-  FLM_LAUNCH_CHECK();
-}
 
 void launch_dw_merge(const DwConv& p, cudaStream_t stream) {
   if (!p.scale || p.B == 0 || p.L == 0) return;
   const int nchunk = dw_nchunk(p.L);
-  if (p.io_bf16 && p.C % 64 == 0)
-    dw_merge_fast_kernel<<<p.B * (p.C / 64), 128, 0, stream>>>(p, nchunk);
-  else
-    dw_merge_kernel<<<(p.B * (p.C / 2) + 127) / 128, 128, 0, stream>>>(p, nchunk);
+  FLM_REQUIRE(p.C % 64 == 0, "dw_merge: C must be a multiple of 64");
+  launch_pdl(dw_merge_fast_kernel, dim3(p.B * (p.C / 64)), dim3(128), (size_t)0, stream, p, nchunk);
   FLM_LAUNCH_CHECK();
 }
 
@@ -988,9 +752,11 @@ void launch_gn_stream(const void* x, void* y, int io_bf16, const float* scale, c
   if (B == 0 || L == 0) return;
   dim3 grid((L + GNS_ROWS - 1) / GNS_ROWS, B);
   if (io_bf16)
-    gn_stream_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), scale, offset, L, C);
+    launch_pdl(gn_stream_kernel<bf16>, grid, dim3(256), (size_t)0, stream, static_cast<const bf16*>(x), static_cast<bf16*>(y), scale,
+               offset, L, C);
   else
-    gn_stream_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), scale, offset, L, C);
+    launch_pdl(gn_stream_kernel<float>, grid, dim3(256), (size_t)0, stream, static_cast<const float*>(x), static_cast<float*>(y), scale,
+               offset, L, C);
   FLM_LAUNCH_CHECK();
 }
 
@@ -999,9 +765,6 @@ void kernels_norm_init() {
   ln_set_attr<1>(); ln_set_attr<2>(); ln_set_attr<3>(); ln_set_attr<4>(); ln_set_attr<8>();
   constexpr int ROWS = DW_TT + 31 - 1;
   FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<float, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 4));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_kernel<bf16, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS * 256 * 2));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * ROWS * 256 * 2 + 64));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<31, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ROWS * 256 * 2 + 64));
 }
 
 void launch_group_stats(const void* x, int x_bf16, int B, int L, int C, int G, float* part, cudaStream_t stream) {

@@ -383,6 +383,8 @@ tapgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_trigger();  // programmatic dependent launch: the set-up above overlapped the previous kernel's tail
+  pdl_wait();
 
   const int kblocks = p.K / BLOCK_K;
   const int iters_per_tile = p.ntaps * kblocks;
@@ -497,7 +499,7 @@ void launch_one(const TapGemm& p, const CUtensorMap& tmA, const CUtensorMap& tmB
                 cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   const int grid = sch.num_tiles < num_sms ? sch.num_tiles : num_sms;
-  tapgemm_tc_kernel<BLOCK_N, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p, sch);
+  launch_pdl(tapgemm_tc_kernel<BLOCK_N, EPI>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, stream, tmA, tmB, p, sch);
   FLM_LAUNCH_CHECK();
 }
 

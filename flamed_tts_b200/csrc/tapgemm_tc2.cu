@@ -332,6 +332,9 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above overlapped the tail of the previous kernel (programmatic dependent launch); its results are needed now
+  pdl_trigger();
+  pdl_wait();
 
   const int kblocks = p.K / BLOCK_K;
   const int iters_per_tile = p.ntaps * kblocks;
@@ -594,7 +597,8 @@ void launch_one(const TapGemm& p, const CUtensorMap* tm, Sched2 sch, int num_sms
   const int smem = 1024 + stages * stage_bytes<BLOCK_N>() + epi_bytes + BAR_BYTES;
   // the dynamic shared-memory opt-in of every instantiation is done per device in tapgemm_tc2_init (flm_ctx_create)
   const int pairs = sch.num_tiles < num_sms / 2 ? sch.num_tiles : num_sms / 2;
-  tapgemm_tc2_kernel<BLOCK_N, EPI><<<2 * pairs, NUM_THREADS, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p, sch);
+  launch_pdl(tapgemm_tc2_kernel<BLOCK_N, EPI>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)smem, stream, tm[0], tm[1], tm[2],
+             tm[3], tm[4], p, sch);
   FLM_LAUNCH_CHECK();
 }
 

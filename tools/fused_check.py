@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Fused LN + depthwise conv + GroupNorm kernel (dwconv_fused.cu) against the unfused kernel chain and the CPU
-oracle on one velocity evaluation, plus timing of both at a bench-sized batch.  usage: python tools/fused_check.py"""
+"""One velocity evaluation of the bf16 denoiser (LayerNorm-fused depthwise conv, programmatic dependent launches)
+against the CPU oracle at edge and bench sizes, reproducibility, and timing per kernel class at bench-sized batches.
+usage: python tools/fused_check.py          (FLAMED_B200_PDL=0 disables the dependent launches for an A/B run)"""
 import os
 import sys
 import time
@@ -26,56 +27,49 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm())
 
 
-def run(x, spk, t, fused):
-    if fused:
-        os.environ.pop("FLAMED_B200_NO_FUSED", None)
-    else:
-        os.environ["FLAMED_B200_NO_FUSED"] = "1"
-    v = den.forward(x.cuda(), t, spk.cuda()).float().cpu()
-    torch.cuda.synchronize()
-    return v
-
-
 ok = True
 for B, L in ((1, 7), (1, 20), (2, 33), (3, 333), (2, 1200), (1, 2400), (5, 64)):
     g = torch.Generator().manual_seed(B * 1000 + L)
     x, spk = torch.randn(B, L, 256, generator=g), torch.randn(B, 256, generator=g)
     with torch.inference_mode():
         ref = O.denoiser_forward(psd, "denoiser", x, torch.full((1, 1), 0.37), spk)
-    vf, vu = run(x, spk, 0.37, True), run(x, spk, 0.37, False)
-    ef, eu, d = rel(vf, ref), rel(vu, ref), rel(vf, vu)
-    good = ef < 1e-2 and bool(torch.isfinite(vf).all())
+    v = den.forward(x.cuda(), 0.37, spk.cuda()).float().cpu()
+    v2 = den.forward(x.cuda(), 0.37, spk.cuda()).float().cpu()
+    e = rel(v, ref)
+    good = e < 1e-2 and bool(torch.isfinite(v).all()) and torch.equal(v, v2)
     ok &= good
-    print("B%d L%d: fused vs oracle %.3e  unfused vs oracle %.3e  fused vs unfused %.3e  %s" % (B, L, ef, eu, d, "ok" if good else "FAIL"),
-          flush=True)
-    vf2 = run(x, spk, 0.37, True)
-    if not torch.equal(vf, vf2):
-        ok = False
-        print("  NOT deterministic")
+    print("B%d L%d: velocity vs oracle %.3e  reproducible %s  %s" % (B, L, e, torch.equal(v, v2), "ok" if good else "FAIL"), flush=True)
 
-# timing at a bench-sized batch (profiler: CUDA events around every launch)
+# 8 Euler steps through sample() (graph capture of dependent launches on the second sighting)
+g = torch.Generator().manual_seed(3)
+B, L, nfe = 2, 150, 8
+cond, spk, noise = torch.relu(torch.randn(B, L, 256, generator=g)), torch.randn(B, 256, generator=g), torch.randn(B, L, 256, generator=g)
+with torch.inference_mode():
+    ref = O.denoiser_sample(sd, "prob_generator", cond, spk, noise, nfe, 0.3).transpose(1, 2)
+ts = torch.linspace(0, 1, nfe + 1)
+a = den.sample(cond, spk, noise, ts, 0.3, use_graph=False).cpu()
+outs = [den.sample(cond, spk, noise, ts, 0.3, use_graph=True).cpu() for _ in range(3)]
+good = rel(a, ref) < 1e-2 and all(torch.equal(a, o) for o in outs)
+ok &= good
+print("8-step loop: vs oracle %.3e, graph == direct %s  %s" % (rel(a, ref), all(torch.equal(a, o) for o in outs), "ok" if good else "FAIL"))
+
 for B, L in ((26, 1225), (62, 520), (64, 1236)):
     g = torch.Generator().manual_seed(1)
     x, spk = torch.randn(B, L, 256, generator=g).cuda(), torch.randn(B, 256, generator=g).cuda()
-    for fused in (True, False):
-        if fused:
-            os.environ.pop("FLAMED_B200_NO_FUSED", None)
-        else:
-            os.environ["FLAMED_B200_NO_FUSED"] = "1"
-        for _ in range(3):
-            den.forward(x, 0.5, spk)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(10):
-            den.forward(x, 0.5, spk)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) / 10 * 1000
-        ctx.profile(True)
-        for _ in range(5):
-            den.forward(x, 0.5, spk)
-        prof = ctx.profile_read()
-        ctx.profile(False)
-        print("B%d L%d fused=%s: %.3f ms per velocity; per class (ms per velocity): %s" % (
-            B, L, fused, wall, {k: round(v["ms"] / 5, 3) for k, v in prof.items()}), flush=True)
+    for _ in range(3):
+        den.forward(x, 0.5, spk)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        den.forward(x, 0.5, spk)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 10 * 1000
+    ctx.profile(True)
+    for _ in range(5):
+        den.forward(x, 0.5, spk)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    print("B%d L%d: %.3f ms per velocity; per class (ms per velocity): %s" % (
+        B, L, wall, {k: round(v["ms"] / 5, 3) for k, v in prof.items()}), flush=True)
 print("ALL OK" if ok else "FAILED")
 sys.exit(0 if ok else 1)

@@ -10,15 +10,14 @@ from torch.profiler import ProfilerActivity, profile  # noqa: E402
 import bench  # noqa: E402
 
 
-class A:
-    utterances, max_batch = 256, 64
-    nsteps_durgen, nsteps_denoiser, temp_durgen, temp_denoiser = 16, int(os.environ.get("NFE", 128)), 0.3, 0.3
-
-
+args = bench.parse_args(["--nsteps-denoiser", os.environ.get("NFE", "128")])
 dev = torch.device("cuda:0")
 cfg, model, enc, dec = bench.build_models(dev, "bf16")
-model.set_noise_device("cuda")
-wl, batches = bench.make_batches(A, 0, model, enc, dec, dev)
+model.set_noise_device("philox")
+wl, n = bench.global_workload(args, 1)
+codes, timbres = bench.prompt_codes(wl, enc, dec, dev)
+batches = bench.host_batches(wl, bench.rank_share(args, wl, 0, 1), codes, timbres)
+A = args
 for b in batches:
     b["dev"] = {k: b[k].to(dev) for k in ("phonemes", "src_lens", "prompts", "timbres")}
 for _ in range(2):
