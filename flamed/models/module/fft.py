@@ -15,12 +15,6 @@ import torch.nn.functional as F
 from flamed.text.symbols import symbols
 
 
-try:  # library attention kernel with per-sample key lengths (flash-attn); optional
-    from flash_attn import flash_attn_with_kvcache as _flash_kvcache
-except Exception:  # noqa: BLE001
-    _flash_kvcache = None
-
-
 def sinusoid_table(n_position, d_hid):
     """pos / 10000^(2*(j//2)/d): sin on even columns, cos on odd (Models.py:10-30)."""
     pos = np.arange(n_position, dtype=np.float64)[:, None]
@@ -93,23 +87,17 @@ class FFTBlock(nn.Module):
                 k1=f.w_1.kernel_size[0], k2=f.w_2.kernel_size[0])
         return self._packed
 
-    def forward_b200(self, ctx, x, pad_u8, attn_bias, key_lens):
-        """x (B,S,D) bf16 contiguous, pad_u8 (B,S) uint8 1 = padding, key_lens (B,) int32 valid prefix length,
-        attn_bias (B,1,1,S) bf16 additive key mask (only used when flash-attn is unavailable)"""
-        from flamed_tts_b200.engines import conv1d_bf16, layernorm_bf16
+    def forward_b200(self, ctx, x, pad_u8, key_lens):
+        """x (B,S,D) bf16 contiguous, pad_u8 (B,S) uint8 1 = padding, key_lens (B,) int32 valid prefix length.
+        Every op is one of the library's kernels: fused q|k|v projection and the other projections / conv-FFN on the
+        tcgen05 implicit-conv GEMM, attention with per-sample key prefixes (flm_attention_bf16), row LayerNorm with
+        the masked_fill of the padding folded in."""
+        from flamed_tts_b200.engines import attention_bf16, conv1d_bf16, layernorm_bf16
         w = self._pack(x.device)
         B, S, D = x.shape
         H = self.slf_attn.n_head
         qkv = conv1d_bf16(ctx, x, w["wqkv"], w["bqkv"]).view(B, S, 3, H, D // H)
-        if _flash_kvcache is not None:
-            # key padding is a PREFIX mask here (lengths), which the library kernel takes as per-sample key counts:
-            # measured 0.91 ms vs 2.35 ms for cuDNN SDPA with an additive mask at B=64, S=1476, 12 heads x 32
-            o = _flash_kvcache(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], cache_seqlens=key_lens, causal=False)
-            o = o.reshape(B, S, D)
-        else:
-            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))             # (B,H,S,dh) strided views
-            o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_bias)
-            o = o.transpose(1, 2).reshape(B, S, D)
+        o = attention_bf16(ctx, qkv, key_lens)
         y = conv1d_bf16(ctx, o, w["wfc"], w["bfc"], epi=4, resid=x)                # fc(o) + x
         x = layernorm_bf16(ctx, y, w["ln1w"], w["ln1b"], self.slf_attn.layer_norm.eps, zero_rows=pad_u8, out=y)
         h = conv1d_bf16(ctx, x, w["w1"], w["b1"], epi=3, off0=-(w["k1"] // 2))      # relu(conv k)
@@ -133,19 +121,15 @@ class _Stack(nn.Module):
 
     def _run(self, x, pad_mask):
         x = x + self._positions(x.shape[1], x.device).to(x.dtype)
-        if self.b200 and x.is_cuda and x.shape[-1] % 128 == 0:
+        if self.b200 and x.is_cuda and x.shape[-1] % 128 == 0 and x.shape[-1] // self.layer_stack[0].slf_attn.n_head == 32:
             from flamed_tts_b200.engines import Context
             ctx = Context.get(x.device)
             out_dtype = x.dtype
             x = x.to(torch.bfloat16).contiguous()
             pad_u8 = pad_mask.to(torch.uint8).contiguous()
-            bias = None
-            if _flash_kvcache is None:
-                bias = torch.zeros((x.shape[0], 1, 1, x.shape[1]), dtype=torch.bfloat16, device=x.device)
-                bias.masked_fill_(pad_mask[:, None, None, :], float("-inf"))
             key_lens = (~pad_mask).sum(1).to(torch.int32)  # get_mask_from_lengths masks are prefix masks
             for blk in self.layer_stack:
-                x = blk.forward_b200(ctx, x, pad_u8, bias, key_lens)
+                x = blk.forward_b200(ctx, x, pad_u8, key_lens)
             return x.to(out_dtype) if out_dtype != torch.bfloat16 else x
         for blk in self.layer_stack:
             x = blk(x, pad_mask)

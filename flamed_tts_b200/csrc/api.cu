@@ -1310,6 +1310,20 @@ extern "C" int flm_layernorm_bf16(flm_ctx* ctx, const void* x, const float* w, c
   FLM_API_END
 }
 
+// o = softmax(q k^T / sqrt(d), keys < key_lens[b]) v per head: the self-attention of the FFT decoder blocks
+// (SubLayers.py:29-57, Modules.py:14-25) on the fused QKV projection's output
+extern "C" int flm_attention_bf16(flm_ctx* ctx, const void* qkv, const int32_t* key_lens, int B, int seq, int H, int dh,
+                                  void* out, flm_stream stream) {
+  FLM_API_BEGIN
+  FLM_REQUIRE(ctx && qkv && key_lens && out, "null argument");
+  FLM_REQUIRE(dh == 32, "attention_bf16: head dim must be 32");
+  DeviceGuard dguard(ctx->device);
+  // 4 B S^2 H d FLOP (QK^T and PV); the op is softmax-bound, profiled under `other`
+  ProfScope ps(ctx, KC_OTHER, S(stream), 4.0 * B * (double)seq * seq * H * dh, 4.0 * B * (double)seq * H * dh * 2, "attention");
+  launch_attn_prefix(static_cast<const bf16*>(qkv), key_lens, B, seq, H, dh, static_cast<bf16*>(out), S(stream));
+  FLM_API_END
+}
+
 // ---- micro-benchmark hook: `reps` back-to-back launches of one tap-GEMM on pseudo-random operands,
 // timed with CUDA events on `stream`; *out_ms = average ms per launch.  epi 0..3, or 5 (gated residual).
 // Operands are pseudo-random (zeros would under-state the power draw and over-state the clocks).

@@ -166,6 +166,9 @@ void launch_conv_in_wav(const float* wav, const float* w, const float* bias, int
 // (B,T,C) -> (B,C,T)
 void launch_transpose_out(const float* x, int B, int T, int C, float* y, cudaStream_t stream);
 
+// ---- self-attention with per-sample key prefixes (attention.cu): qkv (B,S,3,H,32) bf16 -> out (B,S,H*32) bf16
+void launch_attn_prefix(const bf16* qkv, const int32_t* key_lens, int B, int S, int H, int dh, bf16* out, cudaStream_t stream);
+
 // ---- prompt side of the FaCodec decoder (prompt_side.cu): residual vector quantisers + timbre transformer pieces
 constexpr int VQ_MAX_LAYERS = 8;
 constexpr int VQ_MAX_CD = 16;

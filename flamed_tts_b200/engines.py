@@ -358,6 +358,15 @@ def conv1d_bf16(ctx, a, w, bias, epi=0, off0=0, dil=1, resid=None, out=None):
     return out
 
 
+def attention_bf16(ctx, qkv, key_lens):
+    """qkv (B,S,3,H,32) bf16 contiguous, key_lens (B,) int32 -> (B,S,H*32) bf16: softmax(q k^T / sqrt(32)) v over the
+    first key_lens[b] keys of every sample (flm_attention_bf16)"""
+    B, S, three, H, dh = qkv.shape
+    out = torch.empty((B, S, H * dh), device=qkv.device, dtype=torch.bfloat16)
+    check(ctx.lib.flm_attention_bf16(ctx.handle, _ptr(qkv), _ptr(key_lens), B, S, H, dh, _ptr(out), ctx.stream()))
+    return out
+
+
 def layernorm_bf16(ctx, x, w, b, eps, zero_rows=None, out=None):
     """row LayerNorm of x (..., C) bf16 with fp32 affine; rows flagged in zero_rows (uint8/bool, one per row) -> 0"""
     C = x.shape[-1]

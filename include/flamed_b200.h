@@ -227,6 +227,13 @@ int flm_conv1d_bf16(flm_ctx* ctx, const void* A, const void* W, const float* bia
                     int off0, int dil, int epi, void* out, const void* resid, flm_stream stream);
 int flm_layernorm_bf16(flm_ctx* ctx, const void* x, const float* w, const float* b, float eps, int64_t rows, int C,
                        const uint8_t* zero_rows, void* y, flm_stream stream);
+/* replaces: MultiHeadAttention / ScaledDotProductAttention of the FFT decoder blocks (SubLayers.py:29-57,
+ * Modules.py:14-25): out[b,s,h,:] = softmax_k(q.k / sqrt(dh), k < key_lens[b]) v.  qkv (B,S,3,H,dh) bf16 = the
+ * output of the fused q|k|v projection, key_lens (B) i32 device (the key-padding masks of this model are prefix
+ * masks: get_mask_from_lengths), out (B,S,H*dh) bf16; dh must be 32.  Scores never leave registers
+ * (flash-attention dataflow); key tiles beyond a sample's prefix are skipped. */
+int flm_attention_bf16(flm_ctx* ctx, const void* qkv, const int32_t* key_lens, int B, int S, int H, int dh, void* out,
+                       flm_stream stream);
 
 /* bf16-in / bf16-out form of the same problem on the tcgen05 kernels: gen 1 = single-CTA kernel, 2 = CTA-pair
  * (cta_group::2) kernel with the TMA epilogue.  A, W, out, resid, addend are device bf16; bias (N) and gate (B,N)

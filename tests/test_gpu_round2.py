@@ -375,3 +375,32 @@ def test_prompt_side_codes_bit_exact_and_timbre(dropin, codec_dec_sd, golden_dir
         assert _rel(bufs[0], q0) < 1e-5 and _rel(bufs[1], q1) < 1e-5 and _rel(bufs[2], q2) < 1e-5
         assert _rel(outs, q0 + q1 + q2) < 1e-5
     assert _rel(spk, o_spk) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention (f1)
+@pytest.mark.parametrize("B,S,lens", [(3, 200, [200, 1, 65]), (2, 64, [64, 63]), (4, 333, [333, 128, 129, 7]), (2, 1465, [1465, 900])])
+def test_attention_prefix_kernel(ctx, B, S, lens):
+    """flm_attention_bf16 (own flash-style kernel, 12 heads x 32, per-sample key prefixes) against fp64 softmax
+    attention on the same bf16 operands: rel-L2 <= 6e-3 over the valid query rows (probabilities and the output are
+    rounded to bf16), every output finite, masked keys have no influence"""
+    from flamed_tts_b200.engines import attention_bf16
+    H, dh = 12, 32
+    g = torch.Generator().manual_seed(S + B)
+    qkv = (torch.randn(B, S, 3, H, dh, generator=g) * 1.5).to(torch.bfloat16)
+    kl = torch.tensor(lens, dtype=torch.int32)
+    out = attention_bf16(ctx, qkv.to(DEV).contiguous(), kl.to(DEV)).float().cpu()
+    q, k, v = (qkv[:, :, i].double().permute(0, 2, 1, 3) for i in range(3))  # (B,H,S,dh)
+    sc = q @ k.transpose(-1, -2) / dh ** 0.5
+    mask = torch.arange(S)[None, :] >= kl[:, None].long()
+    sc = sc.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, H * dh)
+    assert bool(torch.isfinite(out).all())
+    e = _rel(out, ref)
+    print("attention B=%d S=%d rel-L2 %.3e" % (B, S, e))
+    assert e < 6e-3
+    # keys beyond the prefix must not matter: scramble them and compare bit for bit
+    qkv2 = qkv.clone()
+    for b in range(B):
+        qkv2[b, lens[b]:, 1:] = torch.randn(S - lens[b], 2, H, dh, generator=g).to(torch.bfloat16) * 50
+    out2 = attention_bf16(ctx, qkv2.to(DEV).contiguous(), kl.to(DEV)).float().cpu()
+    assert torch.equal(out, out2)
