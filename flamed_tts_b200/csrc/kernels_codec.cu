@@ -14,7 +14,6 @@ namespace flm {
 
 namespace {
 
-constexpr int ACT_TT = 16;  // outputs per thread along time
 
 template <typename T>
 __device__ __forceinline__ void ldpair(const T* p, float& a, float& b);
@@ -50,12 +49,16 @@ __device__ __forceinline__ f32x2 snake2(f32x2 u2, f32x2 a2, f32x2 ib2) {
   float t0, t1;
   unpack2(mul2(u2, a2), t0, t1);
   const float s0 = FAST ? __sinf(t0) : sinf(t0), s1 = FAST ? __sinf(t1) : sinf(t1);
+  if (FAST) {  // one packed multiply for both squares (the exact path keeps two scalar multiplies: same values, fp32)
+    const f32x2 sn = pack2(s0, s1);
+    return fma2(mul2(sn, sn), ib2, u2);
+  }
   return fma2(pack2(s0 * s0, s1 * s1), ib2, u2);
 }
 
 // u at up-sampled index m (0 <= m < 2T) from the clamped input window xw[i] = x[clamp(n0-5+i)]
 // (static indices only).  q = m - (2*n0 - 5) is the local index; fu2[k] = (2 fu[k], 2 fu[k]).
-template <int Q>
+template <int Q, int ACT_TT>
 __device__ __forceinline__ f32x2 upsample_at(const f32x2 (&xw)[ACT_TT + 10], const f32x2 (&fu2)[12]) {
   f32x2 acc = 0ull;
   if ((Q & 1) == 0) {
@@ -70,20 +73,24 @@ __device__ __forceinline__ f32x2 upsample_at(const f32x2 (&xw)[ACT_TT + 10], con
   return acc;
 }
 
-template <bool FAST, int Q>
+// EDGE: the thread's window touches the ends of the signal (replicate padding of s); interior threads skip the two
+// compare + select pairs per s value (6 ALU instructions each, ~17 % of the instruction stream)
+template <bool FAST, bool EDGE, int ACT_TT, int Q>
 struct SFill {
   __device__ static __forceinline__ void run(const f32x2 (&xw)[ACT_TT + 10], const f32x2 (&fu2)[12], f32x2 a2, f32x2 ib2,
                                              int mbase, int twoT, f32x2 sf, f32x2 sl, f32x2 (&s)[2 * ACT_TT + 10]) {
-    const int m = mbase + Q;
-    f32x2 v = snake2<FAST>(upsample_at<Q>(xw, fu2), a2, ib2);
-    if (m < 0) v = sf;
-    if (m > twoT - 1) v = sl;
+    f32x2 v = snake2<FAST>(upsample_at<Q, ACT_TT>(xw, fu2), a2, ib2);
+    if (EDGE) {
+      const int m = mbase + Q;
+      if (m < 0) v = sf;
+      if (m > twoT - 1) v = sl;
+    }
     s[Q] = v;
-    SFill<FAST, Q + 1>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
+    SFill<FAST, EDGE, ACT_TT, Q + 1>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
   }
 };
-template <bool FAST>
-struct SFill<FAST, 2 * ACT_TT + 10> {
+template <bool FAST, bool EDGE, int ACT_TT>
+struct SFill<FAST, EDGE, ACT_TT, 2 * ACT_TT + 10> {
   __device__ static __forceinline__ void run(const f32x2 (&)[ACT_TT + 10], const f32x2 (&)[12], f32x2, f32x2, int, int,
                                              f32x2, f32x2, f32x2 (&)[2 * ACT_TT + 10]) {}
 };
@@ -97,8 +104,10 @@ __device__ __forceinline__ f32x2 ld_pair2(const T* p) {
 
 // blockDim = (bx channel pairs, by time runs); grid = (C/2/bx, ceil(T/(by*ACT_TT)), B).  The two channels of a
 // thread travel as packed fp32x2 (FFMA2).
-template <typename T, bool FAST>
-__global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
+// CC: compile-time channel count (row stride: the 26 loads and 16 stores of the interior path then use immediate
+// offsets, no address arithmetic in the instruction stream) or 0 for a run-time C
+template <typename T, bool FAST, int ACT_TT, int MINB, int CC>
+__global__ void __launch_bounds__(256, MINB) act1d_kernel(Act1d p) {
   pdl_trigger();
   pdl_wait();
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -115,15 +124,37 @@ __global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
   }
   const f32x2 a2 = *reinterpret_cast<const f32x2*>(p.a + c);
   const f32x2 ib2 = *reinterpret_cast<const f32x2*>(p.invb + c);
+  const int mbase = 2 * n0 - 5;
+  const int twoT = 2 * p.T;
+  T* yb = static_cast<T*>(p.y) + (int64_t)b * p.T * p.C + c;
   f32x2 xw[ACT_TT + 10];
+  f32x2 s[2 * ACT_TT + 10];
+  // interior: the input window [n0-5, n0+ACT_TT+4] and the s window [2 n0 - 5, 2 n0 + 2 ACT_TT + 4] lie inside the signal
+  // (warp-uniform: the lanes of a warp are channel pairs of the same time run)
+  if (n0 - 5 >= 0 && n0 + ACT_TT + 4 <= Tm1) {
+    const int64_t Cs = CC ? CC : p.C;
+    const T* xr = xb + (int64_t)(n0 - 5) * Cs;
+#pragma unroll
+    for (int i = 0; i < ACT_TT + 10; ++i) xw[i] = ld_pair2<T>(xr + i * Cs);
+    SFill<FAST, false, ACT_TT, 0>::run(xw, fu2, a2, ib2, mbase, twoT, 0ull, 0ull, s);
+    T* yr = yb + (int64_t)n0 * Cs;
+#pragma unroll
+    for (int j = 0; j < ACT_TT; ++j) {
+      f32x2 y = 0ull;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) y = fma2(s[2 * j + k], fd2[k], y);
+      float y0, y1;
+      unpack2(y, y0, y1);
+      stpair<T>(yr + j * Cs, y0, y1);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < ACT_TT + 10; ++i) {
     const int t = min(max(n0 - 5 + i, 0), Tm1);
     xw[i] = ld_pair2<T>(xb + (int64_t)t * p.C);
   }
   // replicate padding of the activated up-sampled signal: s[-k] = s[0], s[2T-1+k] = s[2T-1]
-  const int mbase = 2 * n0 - 5;
-  const int twoT = 2 * p.T;
   f32x2 sf = 0ull, sl = 0ull;
   if (mbase < 0) {  // s[0] = snake(u[0]), u[0] = 2*sum x[clamp(-3+i)] fu[11-2i]
     f32x2 u = 0ull;
@@ -137,9 +168,7 @@ __global__ void __launch_bounds__(256) act1d_kernel(Act1d p) {
     for (int i = 0; i < 6; ++i) u = fma2(ld_pair2<T>(xb + (int64_t)min(max(Tm1 - 2 + i, 0), Tm1) * p.C), fu2[10 - 2 * i], u);
     sl = snake2<FAST>(u, a2, ib2);
   }
-  f32x2 s[2 * ACT_TT + 10];
-  SFill<FAST, 0>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
-  T* yb = static_cast<T*>(p.y) + (int64_t)b * p.T * p.C + c;
+  SFill<FAST, true, ACT_TT, 0>::run(xw, fu2, a2, ib2, mbase, twoT, sf, sl, s);
 #pragma unroll
   for (int j = 0; j < ACT_TT; ++j) {
     if (n0 + j < p.T) {
@@ -276,9 +305,8 @@ __global__ void transpose_out_kernel(const float* x, int T_, int C, float* y) {
 
 }  // namespace
 
-void launch_act1d(const Act1d& p, cudaStream_t stream) {
-  FLM_REQUIRE(p.C % 2 == 0, "act1d: C must be even");
-  if (p.B == 0 || p.T == 0) return;
+template <int ACT_TT, int MINB>
+static void launch_act1d_v(const Act1d& p, cudaStream_t stream) {
   int bx = p.C / 2;
   if (bx > 128) bx = 128;
   while ((p.C / 2) % bx) --bx;
@@ -287,14 +315,31 @@ void launch_act1d(const Act1d& p, cudaStream_t stream) {
   dim3 block(bx, by);
   dim3 grid((p.C / 2) / bx, (p.T + by * ACT_TT - 1) / (by * ACT_TT), p.B);
   FLM_REQUIRE(grid.y <= 65535, "act1d: sequence too long");
-  if (p.io_bf16) {
-    if (p.fast_sin) launch_pdl(act1d_kernel<bf16, true>, grid, block, (size_t)0, stream, p);
-    else launch_pdl(act1d_kernel<bf16, false>, grid, block, (size_t)0, stream, p);
+  if (p.io_bf16 && p.fast_sin) {  // throughput mode: one instantiation per channel count of the FaCodec stacks
+    switch (p.C) {
+      case 1024: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 1024>, grid, block, (size_t)0, stream, p); break;
+      case 512: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 512>, grid, block, (size_t)0, stream, p); break;
+      case 256: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 256>, grid, block, (size_t)0, stream, p); break;
+      case 128: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 128>, grid, block, (size_t)0, stream, p); break;
+      case 64: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 64>, grid, block, (size_t)0, stream, p); break;
+      default: launch_pdl(act1d_kernel<bf16, true, ACT_TT, MINB, 0>, grid, block, (size_t)0, stream, p); break;
+    }
+  } else if (p.io_bf16) {
+    launch_pdl(act1d_kernel<bf16, false, ACT_TT, MINB, 0>, grid, block, (size_t)0, stream, p);
   } else {
-    if (p.fast_sin) launch_pdl(act1d_kernel<float, true>, grid, block, (size_t)0, stream, p);
-    else launch_pdl(act1d_kernel<float, false>, grid, block, (size_t)0, stream, p);
+    if (p.fast_sin) launch_pdl(act1d_kernel<float, true, ACT_TT, MINB, 0>, grid, block, (size_t)0, stream, p);
+    else launch_pdl(act1d_kernel<float, false, ACT_TT, MINB, 0>, grid, block, (size_t)0, stream, p);
   }
   FLM_LAUNCH_CHECK();
+}
+
+void launch_act1d(const Act1d& p, cudaStream_t stream) {
+  FLM_REQUIRE(p.C % 2 == 0, "act1d: C must be even");
+  if (p.B == 0 || p.T == 0) return;
+  // 16 outputs per thread at <= 128 registers (two blocks per SM): measured against 8 / 12 outputs per thread and other
+  // register caps on B200 (profiles/r2p/act1d_variants.txt: 16.6 ms per decode of 31.8k frames against 17.1 - 23.6 ms);
+  // the kernel is bound by the fp32 pipes (24 FFMA2 + 4 MUFU per element pair), not by occupancy
+  launch_act1d_v<16, 2>(p, stream);
 }
 
 void launch_conv_out_tanh(const void* x, int x_bf16, const float* w, float bias, int B, int T, int C, float* wav,

@@ -219,8 +219,13 @@ __device__ __forceinline__ void gelu_pair(float& a, float& b) {
   const f32x2 g = fma2(t, phi, pack2(fmaxf(a - ta, 0.0f), fmaxf(b - tb, 0.0f)));
   unpack2(g, a, b);
 }
+// SiLU(x) = x * sigmoid(x) = x * (0.5 + 0.5 * tanh(x / 2)): ONE MUFU op per element (tanh.approx, max relative error
+// 2^-11, i.e. below the bf16 rounding of the result) instead of ex2 + rcp - the SiLU GEMM's epilogue was MUFU-bound
 __device__ __forceinline__ float silu_fast(float x) {
-  return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 template <int EPI>
 __device__ __forceinline__ void act_fast32(float (&v)[32]) {
