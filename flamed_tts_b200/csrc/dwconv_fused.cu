@@ -247,23 +247,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_con
     rc_finish(p, t_lo / nchunk, t, praw + tid * RAW_FLOATS, &rcs[tid]);
   }
   __syncthreads();
-  int cur_b = t_lo / nchunk;
+  // (sample, chunk) of the current tile, of the next one and of the tile the TMA ring prefetches: kept incrementally
+  // (integer divisions by the run-time chunk count cost ~20 instructions each, six of them per tile)
+  int b = t_lo / nchunk, chunk = t_lo % nchunk;
+  int fb = (t_lo + STAGES - 1) / nchunk, fchunk = (t_lo + STAGES - 1) % nchunk;
+  int cur_b = b;
   Affine af = make_affine(p, cur_b, c);
   int slot = 0;
   uint32_t phase = 0;
   for (int tile = t_lo; tile < t_hi; ++tile) {
-    const int b = tile / nchunk, chunk = tile % nchunk;
     const int it = tile - t_lo;
     if (tid == 0) {  // refill the slot drained in the previous iteration (all threads passed its __syncthreads)
-      const int nxt = tile + STAGES - 1;
-      if (nxt < t_hi) {
+      if (tile + STAGES - 1 < t_hi) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const int ns = (slot + STAGES - 1) % STAGES;
-        tma_tile(&tmX, &full[ns], ring + ns * TILE_BYTES, cblk * CB, (nxt % nchunk) * TT - PAD, nxt / nchunk);
+        tma_tile(&tmX, &full[ns], ring + ns * TILE_BYTES, cblk * CB, fchunk * TT - PAD, fb);
       }
     }
+    if (++fchunk == nchunk) { fchunk = 0; ++fb; }
     const bool have_next = tile + 1 < t_hi;
-    const int nb = have_next ? (tile + 1) / nchunk : 0, nt = have_next ? ((tile + 1) % nchunk) * TT - PAD + tid : -1;
+    const int nchunk_next = chunk + 1 == nchunk ? 0 : chunk + 1;
+    const int nb = chunk + 1 == nchunk ? b + 1 : b, nt = nchunk_next * TT - PAD + tid;
     float* raw_next = praw + (((it + 1) & 1) * 64 + tid) * RAW_FLOATS;
     if (have_next && tid < ROWS) rc_prefetch(p, nb, nt, raw_next);
     if (b != cur_b) {  // sample switch (warp-uniform, once or twice per block)
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_con
     }
     __syncthreads();  // the tile slot and the other constants buffer may be overwritten from here on
     if (++slot == STAGES) { slot = 0; phase ^= 1; }
+    b = nb; chunk = nchunk_next;
   }
 }
 

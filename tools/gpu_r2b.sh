@@ -5,4 +5,3 @@ for PDL in 1; do
 FLAMED_B200_PDL=$PDL timeout 300 python tools/fused_check.py > gpurun_out/${TAG}_fused_check_pdl$PDL.txt 2>&1; echo "fused_check_pdl${PDL}_exit=$?"
 tail -13 gpurun_out/${TAG}_fused_check_pdl$PDL.txt | cut -c1-220
 done
-timeout 200 python tools/codec_check.py > gpurun_out/${TAG}_codec_check.txt 2>&1; tail -5 gpurun_out/${TAG}_codec_check.txt | cut -c1-200
