@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflamed_b200.so")
-SOURCES = ["api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "dwconv_fused.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_codec.cu", "comm.cu", "prompt_side.cu", "attention.cu"]
+SOURCES = ["api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_tc2.cu", "dwconv_fused.cu", "dwconv_tc.cu", "kernels_norm.cu", "kernels_misc.cu", "kernels_codec.cu", "comm.cu", "prompt_side.cu", "attention.cu"]
 HEADERS = ["common.cuh", "kernels.h", "engine.h", os.path.join("..", "..", "include", "flamed_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

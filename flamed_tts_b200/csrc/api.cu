@@ -53,6 +53,7 @@ extern "C" int flm_ctx_create(int device, flm_ctx** out) {
   tapgemm_tc_init();
   tapgemm_tc2_init();
   dwconv_fused_init();
+  dwconv_tc_init();
   kernels_norm_init();
   *out = c.release();
   FLM_API_END
@@ -331,7 +332,7 @@ struct flm_denoiser : Engine {
   std::vector<Stage> stages;
   Layer proj_out;
   // buffers
-  DevBuf seed_s, rowstat;
+  DevBuf seed_s, rowstat, rowconst, lnab, lnu;
   DevBuf cond_s, spk_s, noise_s, ts_s, x, xb, h, bufU, bufD, bufG, bufA, part, gsc, gof, gctr, ada, sbuf, temb, tfreq, teh,
       cvec, vout;
   DevBuf c_prior, c_mask, c_xq, c_xm, c_h, c_part, c_sc, c_of, c_out;
@@ -423,10 +424,12 @@ struct flm_denoiser : Engine {
   // bf16 mode with a bf16 residual stream: LayerNorm+modulate, depthwise conv and GroupNorm in one kernel, fed by
   // the row statistics the previous GEMM's epilogue left in `rowstat` (dwconv_fused.cu)
   bool fused() const { return bf(); }
+  // depthwise conv of the fused front half on the tensor cores (dwconv_tc.cu) instead of the FMA pipe (dwconv_fused.cu)
+  bool dw_tensor = [] { const char* e = getenv("FLAMED_B200_DWCONV"); return e && e[0] == 't'; }();
   int rowstat_parts = 0;  // parts written by the last GEMM that produced h
 
-  void ln_dwconv_gn(const ConvNeXtW& c, const float* lnw, const float* lnb, const float* shift, const float* scale, int B,
-                    int L, cudaStream_t s) {
+  void ln_dwconv_gn(const ConvNeXtW& c, const float* lnw, const float* lnb, const float* shift, const float* scale,
+                    const float* gate, int B, int L, cudaStream_t s) {
     DwFused f;
     memset(&f, 0, sizeof(f));
     f.h = h.as<bf16>(); f.u = bufU.as<bf16>(); f.g = bufG.as<bf16>();
@@ -435,6 +438,17 @@ struct flm_denoiser : Engine {
     f.w = c.dw_w; f.wsum = c.dw_wsum; f.bias = c.dw_b; f.gamma = c.gn_w; f.beta = c.gn_b; f.gn_eps = 1e-5f;
     f.B = B; f.L = L; f.C = H; f.tma_encode = ctx->tma_encode;
     const double elems = (double)B * L * H;
+    if (dw_tensor) {  // tensor-core form: statistics merged into gsc / gof by its own last kernel
+      {
+        ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
+        f.u = nullptr;  // conv_3's epilogue recomputes the inner residual from h
+        launch_dwconv_tc(f, rowconst.as<float>(), lnab.as<float>(), part.as<float>(), gsc.as<float>(), gof.as<float>(),
+                         gate, c.conv3.bias, lnu.as<float>(), ctx->num_sms, s);
+      }
+      ProfScope ps(ctx, KC_GN_APPLY, s, elems * 2, elems * 2 * 2);
+      launch_gn_stream(bufG.p, bufG.p, 1, gsc.as<float>(), gof.as<float>(), B, L, H, s);
+      return;
+    }
     {
       ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
       launch_dwconv_ln(f, part.as<float>(), ctx->num_sms, s);
@@ -456,6 +470,10 @@ struct flm_denoiser : Engine {
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
     p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
+    if (fused() && dw_tensor) {  // u recomputed in the epilogue (table written by launch_dwconv_tc)
+      p.addend = nullptr; p.bias = nullptr;
+      p.lnu_rowconst = rowconst.as<float>(); p.lnu_table = lnu.as<float>();
+    }
     p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
     gemm(p, c.conv3, bf(), s);
   }
@@ -525,7 +543,7 @@ struct flm_denoiser : Engine {
       const ResBlockW& rb = blocks[k];
       const float* a = arow + k * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m, gate_m
       if (fz) {
-        ln_dwconv_gn(rb.cn, rb.lnc_w, rb.lnc_b, a, a + H, B, L, s);
+        ln_dwconv_gn(rb.cn, rb.lnc_w, rb.lnc_b, a, a + H, a + 2 * H, B, L, s);
         convnext_tail(rb.cn, B, L, a + 2 * H, s);
       } else {
         ln_modulate(rb.lnc_w, rb.lnc_b, a, a + H, B, L, bufU.p, s);
@@ -543,7 +561,7 @@ struct flm_denoiser : Engine {
     }
     const float* a = arow + blocks.size() * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m
     if (fz) {
-      ln_dwconv_gn(fin, nullptr, nullptr, a, a + H, B, L, s);
+      ln_dwconv_gn(fin, nullptr, nullptr, a, a + H, a + 2 * H, B, L, s);
       convnext_tail(fin, B, L, a + 2 * H, s);
     } else {
       ln_modulate(nullptr, nullptr, a, a + H, B, L, bufU.p, s);
@@ -573,7 +591,8 @@ struct flm_denoiser : Engine {
     moved |= h.ensure(M * H * 4);
     moved |= bufU.ensure(M * H * e); moved |= bufD.ensure(M * H * e); moved |= bufG.ensure(M * H * e);
     moved |= bufA.ensure(M * H * e);
-    moved |= part.ensure((size_t)B * dw_nchunk(L) * H * 2 * 4);
+    moved |= part.ensure(std::max((size_t)B * dw_nchunk(L) * H * 2 * 4, dwconv_tc_part_bytes(B, L, H)));
+    moved |= rowconst.ensure((size_t)M * 8); moved |= lnab.ensure((size_t)B * H * 8); moved |= lnu.ensure((size_t)B * H * 12);
     moved |= gsc.ensure((size_t)B * H * 4); moved |= gof.ensure((size_t)B * H * 4);
     if (gctr.ensure((size_t)B * (H / 256) * 4)) {  // arrival tickets of the depthwise kernel start at zero
       moved = true;

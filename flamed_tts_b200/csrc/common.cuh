@@ -199,6 +199,12 @@ struct TapGemm {
   // of this launch (2 * N / BLOCK_N) on the host.
   float* rowstat;
   int rowstat_parts;
+  // EPI_GATE_RESID on the CTA-pair kernel, alternative to `addend`: the inner residual u = LayerNorm(h) * A + B is
+  // recomputed in the epilogue from the residual-stream slab it holds anyway (h is unchanged since the LayerNorm), so u
+  // is neither written by the depthwise kernel nor read back here.  lnu_rowconst: (rows) float2 (rstd, -mean * rstd);
+  // lnu_table: (B, 3, N) = gate, gate * A, gate * (bias + B) per sample (written by launch_dwconv_tc); `bias` must be null.
+  const float* lnu_rowconst;
+  const float* lnu_table;
 };
 
 // value after bias -> final value; handles every epilogue except the memory side effects

@@ -77,6 +77,14 @@ void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t s
 bool dwconv_fused_supported(const DwFused& p);
 void dwconv_fused_init();
 
+// tensor-core form of the same front half (dwconv_tc.cu): also merges the GroupNorm statistics into scale / offset (B, C).
+// Scratch: rowconst (B*L float2), ab (B*C float2), part (dwconv_tc_part_bytes)
+void launch_dwconv_tc(const DwFused& p, float* rowconst, float* ab, float* part, float* scale, float* offset,
+                      const float* gate, const float* bias3, float* lnu, int num_sms, cudaStream_t stream);
+bool dwconv_tc_supported(const DwFused& p);
+size_t dwconv_tc_part_bytes(int B, int L, int C);
+void dwconv_tc_init();
+
 // ---- generic grouped statistics over (rows x channels-in-group) for GroupNorm(G) in the cond
 //      down-sampler: partials (B, nchunk, G, 2) from chunks of GS_ROWS rows
 constexpr int GS_ROWS = 32;

@@ -52,6 +52,7 @@ struct Sched2 {
   int flatten;
   int stages;         // operand ring depth
   int nbuf;           // epilogue slab buffers
+  int store_depth;    // slab stores whose shared-memory read may still be pending when the next one is issued
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -140,6 +141,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// returns once at most `pending` (0..2) of the committed slab stores have not finished reading shared memory
+__device__ __forceinline__ void tma_store_wait_read_upto(int pending) {
+  if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (pending == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -169,6 +176,19 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
           smem_u32(bar)),
       "h"((uint16_t)3)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -301,11 +321,12 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int vw = warp;  // role index: 0 producer, 1 MMA issuer, 2..9 epilogue, 10 slab loader, 11 slab store
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (vw == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
@@ -326,7 +347,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (vw == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "n"(TMEM_COLS)
                  : "memory");
@@ -344,7 +365,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int kblocks = p.K / BLOCK_K;
   const int iters_per_tile = p.ntaps * kblocks;
 
-  if (warp == 0) {
+  if (vw == 0) {
     // ===================== operand producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
@@ -367,7 +388,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (vw == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BLOCK_N);
@@ -397,10 +418,10 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-  } else if (warp < 2 + NUM_EPI_WARPS) {
+  } else if (vw < 2 + NUM_EPI_WARPS) {
     // ===================== epilogue: thread = row, 32 columns of each 64-column slab =====================
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;     // which 32 columns of the slab
+    const int half = (vw - 2) >> 2;       // which 32 columns of the slab
     const int rrow = quarter * 32 + lane; // row inside the CTA's 128-row tile
     const uint32_t leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
     int it = 0;
@@ -422,6 +443,76 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BLOCK_N);
       f32x2 st_s = 0ull, st_q = 0ull;  // LayerNorm row statistics of this thread's columns of the tile (p.rowstat)
+      if (EPI == EPI_GATE_RESID && p.lnu_table != nullptr) {
+        // inner residual recomputed from the residual-stream slab:  h += G acc + GA (h rstd + nm) + GB
+        f32x2 rs2 = 0ull, nm2 = 0ull;
+        {
+          int64_t grow;
+          bool ok;
+          if (sch.flatten) {
+            grow = (int64_t)mt * BLOCK_M + rrow;
+            ok = grow < (int64_t)p.B * p.T_out;
+          } else {
+            const int tb = mt / sch.tiles_m_per_b, tr = (mt % sch.tiles_m_per_b) * BLOCK_M + rrow;
+            grow = (int64_t)tb * p.T_out + tr;
+            ok = tb < p.B && tr < p.T_out;
+          }
+          if (ok) {
+            const float2 rc = __ldg(reinterpret_cast<const float2*>(p.lnu_rowconst) + grow);
+            rs2 = pack2(rc.x, rc.x);
+            nm2 = pack2(rc.y, rc.y);
+          }
+        }
+        const float* tab = p.lnu_table + (int64_t)bidx * 3 * p.N;
+#pragma unroll 1
+        for (int s = 0; s < SLABS; ++s) {
+          uint8_t* rrow_ptr = smem_r + buf * SLAB_BYTES + rrow * 128;
+#pragma unroll 1
+          for (int q = 0; q < 2; ++q) {
+            const int n = nt * BLOCK_N + s * SLAB_COLS + half * 32 + q * 16;
+            float4 G[4], GA[4], GB[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              G[j] = __ldg(reinterpret_cast<const float4*>(tab + n) + j);
+              GA[j] = __ldg(reinterpret_cast<const float4*>(tab + p.N + n) + j);
+              GB[j] = __ldg(reinterpret_cast<const float4*>(tab + 2 * p.N + n) + j);
+            }
+            float v[16];
+            tmem_ld16(taddr + (uint32_t)(s * SLAB_COLS + half * 32 + q * 16), v);
+            if (q == 0) mbar_wait(&r_full[buf], bphase);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint4* slot = reinterpret_cast<uint4*>(rrow_ptr + (((half * 4 + q * 2 + c) ^ (rrow & 7)) << 4));
+              const uint4 hq = *slot;
+              const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const f32x2 h2 = pack2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
+                const f32x2 acc2 = pack2(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
+                const float4 g = G[c * 2 + (j >> 1)], ga = GA[c * 2 + (j >> 1)], gb = GB[c * 2 + (j >> 1)];
+                const f32x2 t2 = fma2(h2, rs2, nm2);
+                f32x2 r2 = fma2((j & 1) ? pack2(g.z, g.w) : pack2(g.x, g.y), acc2, h2);
+                r2 = fma2((j & 1) ? pack2(ga.z, ga.w) : pack2(ga.x, ga.y), t2, r2);
+                r2 = add2(r2, (j & 1) ? pack2(gb.z, gb.w) : pack2(gb.x, gb.y));
+                if (p.rowstat) {
+                  st_s = add2(st_s, r2);
+                  st_q = fma2(r2, r2, st_q);
+                }
+                float lo, hi;
+                unpack2(r2, lo, hi);
+                __nv_bfloat162 tt = __floats2bfloat162_rn(lo, hi);
+                o[j] = *reinterpret_cast<uint32_t*>(&tt);
+              }
+              *slot = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&r_ready[buf]);
+          if (++buf == sch.nbuf) { buf = 0; bphase ^= 1; }
+        }
+      } else {
 #pragma unroll 1
       for (int s = 0; s < SLABS; ++s) {
         const int n = nt * BLOCK_N + s * SLAB_COLS + half * 32;
@@ -512,6 +603,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) mbar_arrive(&r_ready[buf]);
         if (++buf == sch.nbuf) { buf = 0; bphase ^= 1; }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
@@ -535,7 +627,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
     }
-  } else if (warp == 2 + NUM_EPI_WARPS) {
+  } else if (vw == 2 + NUM_EPI_WARPS) {
     // ===================== epilogue operand loader =====================
     if (kResid && lane == 0) {
       int buf = 0;
@@ -555,8 +647,12 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else {
     // ===================== slab store =====================
+    // Up to `store_depth` stores stay in flight: waiting for each store's shared-memory read before looking at the next
+    // slab serialised the four slabs of a tile on the store latency.  Bulk groups complete in order, so once at most
+    // `depth` groups are pending the buffer of the store issued `depth` slabs ago is reusable.
     if (lane == 0) {
-      int buf = 0;
+      const int depth = sch.store_depth;
+      int buf = 0, fbuf = 0, inflight = 0;
       uint32_t bphase = 0;
       for (int tile = pair; tile < sch.num_tiles; tile += npairs) {
         const int nt = tile % sch.num_n_tiles, mp = tile / sch.num_n_tiles;
@@ -565,10 +661,19 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           mbar_wait(&r_ready[buf], bphase);
           tma_store_3d(&tmO, smem_r + buf * SLAB_BYTES, nt * BLOCK_N + s * SLAB_COLS, tr.row, tr.b);
           tma_store_commit();
-          tma_store_wait_read();
-          mbar_arrive(&r_free[buf]);
           if (++buf == sch.nbuf) { buf = 0; bphase ^= 1; }
+          if (++inflight > depth) {
+            tma_store_wait_read_upto(depth);
+            mbar_arrive(&r_free[fbuf]);
+            if (++fbuf == sch.nbuf) fbuf = 0;
+            --inflight;
+          }
         }
+      }
+      tma_store_wait_read();
+      for (; inflight > 0; --inflight) {
+        mbar_arrive(&r_free[fbuf]);
+        if (++fbuf == sch.nbuf) fbuf = 0;
       }
       tma_store_wait_all();  // global writes complete before the CTA retires
     }
@@ -576,7 +681,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_before();
   __syncthreads();
   cluster_sync();  // the peer may still multicast into / read from this CTA's shared memory until here
-  if (warp == 1) {
+  if (vw == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -595,6 +700,7 @@ void launch_one(const TapGemm& p, const CUtensorMap* tm, Sched2 sch, int num_sms
   const bool resid = epi_loads_residual(EPI);
   // slab buffers: enough loads in flight to cover HBM latency at the tensor-core rate; the rest goes to the ring
   sch.nbuf = addend ? 3 : (resid ? 4 : 3);
+  sch.store_depth = 1;  // (measured: 0, 1 and 2 are within noise of each other, profiles/r2w)
   const int epi_bytes = sch.nbuf * SLAB_BYTES * (addend ? 2 : 1);
   int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - epi_bytes) / stage_bytes<BLOCK_N>();
   if (stages > MAX_STAGES) stages = MAX_STAGES;
