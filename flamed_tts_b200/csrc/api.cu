@@ -437,11 +437,12 @@ struct flm_denoiser : Engine {
     f.ln_w = lnw; f.ln_b = lnb; f.shift = shift; f.scale = scale; f.mod_bstride = ada_n; f.ln_eps = 1e-6f;
     f.w = c.dw_w; f.wsum = c.dw_wsum; f.bias = c.dw_b; f.gamma = c.gn_w; f.beta = c.gn_b; f.gn_eps = 1e-5f;
     f.B = B; f.L = L; f.C = H; f.tma_encode = ctx->tma_encode;
+    // the inner residual u is not written: conv_3's epilogue recomputes it from h (TapGemm::lnu_*)
+    f.u = nullptr;
     const double elems = (double)B * L * H;
     if (dw_tensor) {  // tensor-core form: statistics merged into gsc / gof by its own last kernel
       {
-        ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
-        f.u = nullptr;  // conv_3's epilogue recomputes the inner residual from h
+        ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 4);
         launch_dwconv_tc(f, rowconst.as<float>(), lnab.as<float>(), part.as<float>(), gsc.as<float>(), gof.as<float>(),
                          gate, c.conv3.bias, lnu.as<float>(), ctx->num_sms, s);
       }
@@ -450,7 +451,8 @@ struct flm_denoiser : Engine {
       return;
     }
     {
-      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 6);
+      f.rowconst_out = rowconst.as<float>(); f.lnu_out = lnu.as<float>(); f.gate = gate; f.bias3 = c.conv3.bias;
+      ProfScope ps(ctx, KC_DWCONV, s, elems * 2 * (cfg.kernel_size + 2), elems * 4);
       launch_dwconv_ln(f, part.as<float>(), ctx->num_sms, s);
       DwConv dw;
       memset(&dw, 0, sizeof(dw));
@@ -470,7 +472,7 @@ struct flm_denoiser : Engine {
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
     p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
-    if (fused() && dw_tensor) {  // u recomputed in the epilogue (table written by launch_dwconv_tc)
+    if (fused()) {  // u recomputed in the epilogue (row constants and table written by the depthwise kernel)
       p.addend = nullptr; p.bias = nullptr;
       p.lnu_rowconst = rowconst.as<float>(); p.lnu_table = lnu.as<float>();
     }

@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
 // per velocity against 0.486 ms for a single always-masked variant (B=26, L=1225; profiles/r2h).
 // CC: compile-time channel count (row stride of the outputs: the 64 stores of a tile then use immediate offsets from two
 // base registers, no pointer arithmetic on the issue slots), or 0 for a run-time C.
-template <bool MASKED, int CC, typename Mid>
+template <bool MASKED, bool WRITE_U, int CC, typename Mid>
 __device__ __forceinline__ void conv_tile(const bf16* __restrict__ xs, const float4* __restrict__ rc,
                                           const f32x2 (&w2)[KW], f32x2 A2, f32x2 B2, f32x2 acc0, f32x2 ob2, int nvalid,
                                           int Crt, bf16* __restrict__ ub, bf16* __restrict__ gb, f32x2& S1, f32x2& S2,
@@ -108,7 +108,7 @@ __device__ __forceinline__ void conv_tile(const bf16* __restrict__ xs, const flo
       Bz = pack2(inside ? b0 : 0.f, inside ? b1 : 0.f);
     }
     const f32x2 u2 = fma2(fma2(x2, rr, mm), A2, Bz);
-    if (r >= PAD && r < PAD + TT) {  // centre rows: this tile owns them -> inner-residual operand of conv_3
+    if (WRITE_U && r >= PAD && r < PAD + TT) {  // centre rows: this tile owns them -> inner-residual operand of conv_3
       if (!MASKED || r - PAD < nvalid) *reinterpret_cast<uint32_t*>(ub + (r - PAD) * C) = f32x2_to_bf16x2(u2);
     }
 #pragma unroll
@@ -209,7 +209,7 @@ __device__ __forceinline__ Affine make_affine(const DwFused& p, int b, int c) {
 
 // persistent blocks over contiguous (sample, chunk) tile ranges; per-chunk (mean, M2) partial statistics out (layout
 // (B, nchunk, C, 2), the layout launch_dw_merge consumes)
-template <int CC>
+template <int CC, bool WU>
 __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwFused p,
                                                                 float* __restrict__ part, int nchunk, int ncblk,
                                                                 int ntiles) {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_con
     mbar_wait(&full[slot], phase);
     const int t0 = chunk * TT;
     const bf16* xs = reinterpret_cast<const bf16*>(ring + slot * TILE_BYTES) + tid * 2;
-    bf16* ub = p.u + ((int64_t)b * p.L + t0) * p.C + c;
+    bf16* ub = WU ? p.u + ((int64_t)b * p.L + t0) * p.C + c : nullptr;
     bf16* gb = p.g + ((int64_t)b * p.L + t0) * p.C + c;
     f32x2 T1 = 0ull, T2 = 0ull;
     const float4* rc = rcs + (it & 1) * 64;
@@ -285,8 +285,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_con
       if (have_next && tid < ROWS) rc_finish(p, nb, nt, raw_next, &rcs[((it + 1) & 1) * 64 + tid]);
     };
     const bool interior = (t0 - PAD >= 0) && (t0 + TT + PAD <= p.L);
-    if (interior) conv_tile<false, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, TT, p.C, ub, gb, T1, T2, mid);
-    else conv_tile<true, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, min(TT, p.L - t0), p.C, ub, gb, T1, T2, mid);
+    if (WU) {
+      if (interior) conv_tile<false, true, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, TT, p.C, ub, gb, T1, T2, mid);
+      else conv_tile<true, true, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, min(TT, p.L - t0), p.C, ub, gb, T1, T2, mid);
+    } else {
+      if (interior) conv_tile<false, false, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, TT, p.C, ub, gb, T1, T2, mid);
+      else conv_tile<true, false, CC>(xs, rc, w2, af.A2, af.B2, af.acc0, af.ob2, min(TT, p.L - t0), p.C, ub, gb, T1, T2, mid);
+      // by-products for conv_3's epilogue: the LayerNorm constants of the rows this tile owns (one channel block writes
+      // them) and, on the first chunk of a sample, the (gate, gate A, gate (bias3 + B)) entries of this thread's channels
+      if (cblk == 0 && tid >= PAD && tid < PAD + TT && t0 + tid - PAD < p.L) {
+        const float4 q = rc[tid];
+        reinterpret_cast<float2*>(p.rowconst_out)[(int64_t)b * p.L + t0 + tid - PAD] = make_float2(q.x, q.z);
+      }
+      if (chunk == 0) {
+        const float2 g = *reinterpret_cast<const float2*>(p.gate + (int64_t)b * p.mod_bstride + c);
+        const float2 b3 = *reinterpret_cast<const float2*>(p.bias3 + c);
+        float a0, a1, b0, b1;
+        unpack2(af.A2, a0, a1);
+        unpack2(af.B2, b0, b1);
+        float* t = p.lnu_out + (int64_t)b * 3 * p.C + c;
+        *reinterpret_cast<float2*>(t) = g;
+        *reinterpret_cast<float2*>(t + p.C) = make_float2(g.x * a0, g.y * a1);
+        *reinterpret_cast<float2*>(t + 2 * p.C) = make_float2(g.x * (b3.x + b0), g.y * (b3.y + b1));
+      }
+    }
     {  // per-chunk (mean, M2) about the pivot: mean = pivot + S/n, M2 = Q - S^2/n
       float s0, s1, q0, q1;
       unpack2(T1, s0, s1);
@@ -309,14 +331,17 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 }  // namespace
 
 void dwconv_fused_init() {
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  FLM_CUDA(cudaFuncSetAttribute(dwconv_ln_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
 }
 
 bool dwconv_fused_supported(const DwFused& p) {
   return p.C % CB == 0 && p.rowstat != nullptr && p.parts >= 2 && p.parts % 2 == 0 && p.tma_encode != nullptr &&
          (reinterpret_cast<uintptr_t>(p.h) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.g) & 3) == 0 &&
-         (reinterpret_cast<uintptr_t>(p.u) & 3) == 0;
+         (reinterpret_cast<uintptr_t>(p.u) & 3) == 0 &&
+         (p.u != nullptr || (p.rowconst_out && p.lnu_out && p.gate && p.bias3 && p.scale));
 }
 
 // LayerNorm-on-load + depthwise conv, persistent; writes u, the un-normalised d (into p.g) and the per-chunk partial
@@ -338,12 +363,11 @@ void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t s
   int slices = (2 * num_sms) / ncblk;
   if (slices > ntiles) slices = ntiles;
   if (slices < 1) slices = 1;
-  if (p.C == 1024)
-    launch_pdl(dwconv_ln_kernel<1024>, dim3(slices * ncblk), dim3(NTHREADS), (size_t)SMEM_BYTES, stream, tm, p, part, nchunk, ncblk,
-               ntiles);
-  else
-    launch_pdl(dwconv_ln_kernel<0>, dim3(slices * ncblk), dim3(NTHREADS), (size_t)SMEM_BYTES, stream, tm, p, part, nchunk, ncblk,
-               ntiles);
+  auto go = [&](auto kernel) {
+    launch_pdl(kernel, dim3(slices * ncblk), dim3(NTHREADS), (size_t)SMEM_BYTES, stream, tm, p, part, nchunk, ncblk, ntiles);
+  };
+  if (p.C == 1024) { if (p.u) go(dwconv_ln_kernel<1024, true>); else go(dwconv_ln_kernel<1024, false>); }
+  else { if (p.u) go(dwconv_ln_kernel<0, true>); else go(dwconv_ln_kernel<0, false>); }
   FLM_LAUNCH_CHECK();
 }
 

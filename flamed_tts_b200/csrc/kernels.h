@@ -72,6 +72,12 @@ struct DwFused {
   const float* gamma; const float* beta; float gn_eps;  // GroupNorm affine
   int B, L, C;
   void* tma_encode;
+  // optional by-products for conv_3's epilogue (TapGemm::lnu_rowconst / lnu_table), all null or all set together with
+  // u == nullptr: the inner residual u is then recomputed there instead of being written here
+  float* rowconst_out;   // (B*L) float2 (rstd, -mean * rstd)
+  float* lnu_out;        // (B, 3, C): gate, gate * A, gate * (bias3 + B)
+  const float* gate;     // adaLN gate of the block, sample stride mod_bstride
+  const float* bias3;    // conv_3's bias (C)
 };
 void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t stream);
 bool dwconv_fused_supported(const DwFused& p);
