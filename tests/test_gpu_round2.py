@@ -404,3 +404,47 @@ def test_attention_prefix_kernel(ctx, B, S, lens):
         qkv2[b, lens[b]:, 1:] = torch.randn(S - lens[b], 2, H, dh, generator=g).to(torch.bfloat16) * 50
     out2 = attention_bf16(ctx, qkv2.to(DEV).contiguous(), kl.to(DEV)).float().cpu()
     assert torch.equal(out, out2)
+
+
+# ------------------------------------------------------------------------------------------------ opt-in depthwise kernel
+_DWTC_SCRIPT = r"""
+import os, sys, torch, yaml
+sys.path.insert(0, %(root)r)
+from flamed_tts_b200 import synthetic as W
+from flamed_tts_b200.engines import Context, DenoiserEngine
+from oracle import flamed_oracle as O
+root = %(root)r
+prior = yaml.safe_load(open(os.path.join(root, "configs", "prior.yaml")))
+prob = yaml.safe_load(open(os.path.join(root, "configs", "prob.yaml")))
+sd = W.make_flamed_state_dict(prior, prob, 0)
+psd = {k[len("prob_generator."):]: v for k, v in sd.items() if k.startswith("prob_generator.")}
+den = DenoiserEngine(Context.get("cuda:0"), psd, prob, "bf16")
+worst = 0.0
+for B, L in ((1, 7), (3, 97), (2, 1200), (5, 64)):
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    x, spk = torch.randn(B, L, 256, generator=g), torch.randn(B, 256, generator=g)
+    with torch.inference_mode():
+        ref = O.denoiser_forward(psd, "denoiser", x, torch.full((1, 1), 0.37), spk)
+    v = den.forward(x.cuda(), 0.37, spk.cuda()).float().cpu()
+    v2 = den.forward(x.cuda(), 0.37, spk.cuda()).float().cpu()
+    assert torch.equal(v, v2), "not reproducible"
+    e = float((v.double() - ref.double()).norm() / ref.double().norm())
+    worst = max(worst, e)
+print("WORST %%.4e" %% worst)
+"""
+
+
+def test_tensor_core_depthwise_path_matches_the_oracle():
+    """FLAMED_B200_DWCONV=tc: the depthwise conv of the ConvNeXt blocks on the tensor cores (dwconv_tc.cu: Hankel operand
+    out of a channel time series, TMA-staged input, ldmatrix transposition, packed-bf16 LayerNorm) instead of the FMA
+    kernel.  Same bf16 tolerance as the production path (1e-2), at edge lengths (tiles that straddle samples, rows
+    shorter than the conv window) and at a bench-sized frame count.  The switch is read when a denoiser handle is
+    created, hence the subprocess."""
+    import subprocess
+    import sys
+    env = dict(os.environ, FLAMED_B200_DWCONV="tc")
+    r = subprocess.run([sys.executable, "-c", _DWTC_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    worst = float(r.stdout.strip().splitlines()[-1].split()[1])
+    print("tensor-core depthwise path: worst velocity rel-L2 %.3e" % worst)
+    assert worst < 1e-2
