@@ -332,7 +332,7 @@ struct flm_denoiser : Engine {
   std::vector<Stage> stages;
   Layer proj_out;
   // buffers
-  DevBuf seed_s, rowstat, rowconst, lnab, lnu;
+  DevBuf seed_s, rowstat, rowconst, lnab, lnu, s1buf, s2buf, c1tab, c2tab;
   DevBuf cond_s, spk_s, noise_s, ts_s, x, xb, h, bufU, bufD, bufG, bufA, part, gsc, gof, gctr, ada, sbuf, temb, tfreq, teh,
       cvec, vout;
   DevBuf c_prior, c_mask, c_xq, c_xm, c_h, c_part, c_sc, c_of, c_out;
@@ -426,10 +426,14 @@ struct flm_denoiser : Engine {
   bool fused() const { return bf(); }
   // depthwise conv of the fused front half on the tensor cores (dwconv_tc.cu) instead of the FMA pipe (dwconv_fused.cu)
   bool dw_tensor = [] { const char* e = getenv("FLAMED_B200_DWCONV"); return e && e[0] == 't'; }();
+  // MLP-branch LayerNorm applied algebraically (no pass of its own): conv_3's epilogue also writes A2 * h', mlp.0 runs on
+  // it and its epilogue applies the per-row part (TapGemm::raff_*)
+  bool mlp_ln_fused = [] { const char* e = getenv("FLAMED_B200_MLPLN"); return !(e && e[0] == '0'); }();
+  int rowstat3_parts = 0;  // parts written by the last conv_3
   int rowstat_parts = 0;  // parts written by the last GEMM that produced h
 
   void ln_dwconv_gn(const ConvNeXtW& c, const float* lnw, const float* lnb, const float* shift, const float* scale,
-                    const float* gate, int B, int L, cudaStream_t s) {
+                    const float* gate, const float* ln2_w, const float* scale2, int B, int L, cudaStream_t s) {
     DwFused f;
     memset(&f, 0, sizeof(f));
     f.h = h.as<bf16>(); f.u = bufU.as<bf16>(); f.g = bufG.as<bf16>();
@@ -439,6 +443,7 @@ struct flm_denoiser : Engine {
     f.B = B; f.L = L; f.C = H; f.tma_encode = ctx->tma_encode;
     // the inner residual u is not written: conv_3's epilogue recomputes it from h (TapGemm::lnu_*)
     f.u = nullptr;
+    f.lnu_vecs = scale2 ? 4 : 3; f.ln2_w = ln2_w; f.scale2 = scale2;
     const double elems = (double)B * L * H;
     if (dw_tensor) {  // tensor-core form: statistics merged into gsc / gof by its own last kernel
       {
@@ -467,14 +472,19 @@ struct flm_denoiser : Engine {
   }
 
   // conv_2 (GELU) + conv_3 (gated residual with the inner residual u): hres += gate * (u + conv3(gelu(conv2(g))))
-  void convnext_tail(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s) {
+  void convnext_tail(const ConvNeXtW& c, int B, int L, const float* gate, cudaStream_t s, bool scaled_copy = false) {
     const int b16 = bf() ? 1 : 0;
     gemm(problem(c.conv2, bufG.p, H, B, L, L, bufA.p, H, b16, EPI_GELU), c.conv2, bf(), s);
     TapGemm p = problem(c.conv3, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
     p.gate = gate; p.gate_bstride = ada_n; p.addend = bufU.p; p.ld_add = H; p.addend_bf16 = b16;
     if (fused()) {  // u recomputed in the epilogue (row constants and table written by the depthwise kernel)
       p.addend = nullptr; p.bias = nullptr;
-      p.lnu_rowconst = rowconst.as<float>(); p.lnu_table = lnu.as<float>();
+      p.lnu_rowconst = rowconst.as<float>(); p.lnu_table = lnu.as<float>(); p.lnu_vecs = scaled_copy ? 4 : 3;
+      if (scaled_copy) {  // A2 * h' for mlp.0 and the row statistics of h' for its epilogue
+        p.out2 = bufU.p; p.ld_out2 = H;
+        p.rowstat = rowstat.as<float>();
+        p.rowstat_parts = rowstat3_parts = tapgemm_tc2_rowstat_parts(p, ctx->num_sms);
+      }
     }
     p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
     gemm(p, c.conv3, bf(), s);
@@ -514,13 +524,28 @@ struct flm_denoiser : Engine {
 
   // adaLN table for `nfe` time points: ada[(i*B+b), :]   (hoisted out of the loop)
   void modulation_table(int B, int nfe, cudaStream_t s) {
+    table_rows = nfe * B;
     launch_timestep_embedding(ts_s.as<float>(), nfe, 256, tfreq.as<float>(), s);
     gemm(problem(time0, tfreq.p, 256, 1, nfe, nfe, teh.p, H, 0, EPI_SILU), time0, false, s);
     gemm(problem(time2, teh.p, H, 1, nfe, nfe, temb.p, H, 0, EPI_NONE), time2, false, s);
     gemm(problem(cond_embed, spk_s.p, cfg.spk_dim, 1, B, B, cvec.p, H, 0, EPI_NONE), cond_embed, false, s);
     launch_silu_sum(temb.as<float>(), cvec.as<float>(), nfe, B, H, sbuf.p, bf() ? 1 : 0, s);
     gemm(problem(ada_all, sbuf.p, H, 1, nfe * B, nfe * B, ada.p, ada_n, 0, EPI_NONE), ada_all, bf(), s);
+    if (fused() && mlp_ln_fused) {
+      // c1 = W0 . A2, c2 = W0 . B2 + b0 for every (step, sample) of every block: the column part of the MLP-branch LayerNorm
+      const int64_t rows = (int64_t)nfe * B;
+      for (size_t k = 0; k < blocks.size(); ++k) {
+        const ResBlockW& rb = blocks[k];
+        const float* a = ada.as<float>() + k * 6 * H;
+        launch_ln_affine_rows(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, ada_n, rows, H, s1buf.as<bf16>(), s2buf.as<bf16>(), s);
+        TapGemm p1 = problem(rb.mlp0, s1buf.p, H, 1, (int)rows, (int)rows, c1tab.as<float>() + k * rows * H, H, 0, EPI_NONE);
+        p1.bias = nullptr;
+        gemm(p1, rb.mlp0, true, s);
+        gemm(problem(rb.mlp0, s2buf.p, H, 1, (int)rows, (int)rows, c2tab.as<float>() + k * rows * H, H, 0, EPI_NONE), rb.mlp0, true, s);
+      }
+    }
   }
+  int table_rows = 0;  // nfe * B of the current modulation table
 
   // one velocity evaluation at table row `i`, accumulated as target += alpha * v
   void step(int B, int L, int i, float* target, float alpha, cudaStream_t s) {
@@ -544,15 +569,25 @@ struct flm_denoiser : Engine {
     for (size_t k = 0; k < blocks.size(); ++k) {
       const ResBlockW& rb = blocks[k];
       const float* a = arow + k * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m, gate_m
+      const bool mf = fz && mlp_ln_fused;
       if (fz) {
-        ln_dwconv_gn(rb.cn, rb.lnc_w, rb.lnc_b, a, a + H, a + 2 * H, B, L, s);
-        convnext_tail(rb.cn, B, L, a + 2 * H, s);
+        ln_dwconv_gn(rb.cn, rb.lnc_w, rb.lnc_b, a, a + H, a + 2 * H, mf ? rb.lnm_w : nullptr, mf ? a + 4 * H : nullptr, B, L, s);
+        convnext_tail(rb.cn, B, L, a + 2 * H, s, mf);
       } else {
         ln_modulate(rb.lnc_w, rb.lnc_b, a, a + H, B, L, bufU.p, s);
         convnext(rb.cn, B, L, a + 2 * H, s);
       }
-      ln_modulate(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
-      gemm(problem(rb.mlp0, bufU.p, H, B, L, L, bufA.p, H, b16, EPI_SILU), rb.mlp0, bf(), s);
+      TapGemm p0 = problem(rb.mlp0, bufU.p, H, B, L, L, bufA.p, H, b16, EPI_SILU);
+      if (mf) {  // LayerNorm + modulate of the MLP branch applied algebraically in mlp.0's epilogue
+        const int64_t trow = ((int64_t)k * table_rows + (int64_t)i * B) * H;
+        p0.bias = nullptr;
+        p0.raff_rowstat = rowstat.as<float>(); p0.raff_parts = rowstat3_parts;
+        p0.raff_c1 = c1tab.as<float>() + trow; p0.raff_c2 = c2tab.as<float>() + trow;
+        p0.raff_eps = 1e-6f; p0.raff_ln_dim = H;
+      } else {
+        ln_modulate(rb.lnm_w, rb.lnm_b, a + 3 * H, a + 4 * H, B, L, bufU.p, s);
+      }
+      gemm(p0, rb.mlp0, bf(), s);
       TapGemm p = problem(rb.mlp2, bufA.p, H, B, L, L, nullptr, H, 0, EPI_GATE_RESID);
       p.gate = a + 5 * H; p.gate_bstride = ada_n; p.hres = h.as<float>(); p.ld_res = H; p.hres_bf16 = h16 ? 1 : 0;
       if (fz) {  // row statistics of the updated h for the next block's (or the final layer's) fused kernel
@@ -563,7 +598,7 @@ struct flm_denoiser : Engine {
     }
     const float* a = arow + blocks.size() * 6 * H;  // shift_c, scale_c, gate_c, shift_m, scale_m
     if (fz) {
-      ln_dwconv_gn(fin, nullptr, nullptr, a, a + H, a + 2 * H, B, L, s);
+      ln_dwconv_gn(fin, nullptr, nullptr, a, a + H, a + 2 * H, nullptr, nullptr, B, L, s);
       convnext_tail(fin, B, L, a + 2 * H, s);
     } else {
       ln_modulate(nullptr, nullptr, a, a + H, B, L, bufU.p, s);
@@ -594,7 +629,11 @@ struct flm_denoiser : Engine {
     moved |= bufU.ensure(M * H * e); moved |= bufD.ensure(M * H * e); moved |= bufG.ensure(M * H * e);
     moved |= bufA.ensure(M * H * e);
     moved |= part.ensure(std::max((size_t)B * dw_nchunk(L) * H * 2 * 4, dwconv_tc_part_bytes(B, L, H)));
-    moved |= rowconst.ensure((size_t)M * 8); moved |= lnab.ensure((size_t)B * H * 8); moved |= lnu.ensure((size_t)B * H * 12);
+    moved |= rowconst.ensure((size_t)M * 8); moved |= lnab.ensure((size_t)B * H * 8); moved |= lnu.ensure((size_t)B * H * 16);
+    if (fused() && mlp_ln_fused) {
+      moved |= s1buf.ensure((size_t)nfe * B * H * 2); moved |= s2buf.ensure((size_t)nfe * B * H * 2);
+      moved |= c1tab.ensure(blocks.size() * (size_t)nfe * B * H * 4); moved |= c2tab.ensure(blocks.size() * (size_t)nfe * B * H * 4);
+    }
     moved |= gsc.ensure((size_t)B * H * 4); moved |= gof.ensure((size_t)B * H * 4);
     if (gctr.ensure((size_t)B * (H / 256) * 4)) {  // arrival tickets of the depthwise kernel start at zero
       moved = true;

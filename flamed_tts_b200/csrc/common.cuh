@@ -205,6 +205,21 @@ struct TapGemm {
   // lnu_table: (B, 3, N) = gate, gate * A, gate * (bias + B) per sample (written by launch_dwconv_tc); `bias` must be null.
   const float* lnu_rowconst;
   const float* lnu_table;
+  // ... and, with lnu_table holding a 4th vector A2 (lnu_vecs == 4), a second bf16 output out2 = A2[b,n] * (updated h):
+  // the column-scaled copy of the residual stream the NEXT LayerNorm's GEMM runs on (see raff_*)
+  void* out2;
+  int64_t ld_out2;
+  int lnu_vecs;  // 3 or 4
+  // EPI_SILU on the CTA-pair kernel: LayerNorm of the PREVIOUS layer applied algebraically.  A = A2 * h (out2 above),
+  //   value = rstd_r * acc + nm_r * c1[b,n] + c2[b,n],   c1 = W . A2_b,  c2 = W . B2_b + bias  (`bias` must be null),
+  // with (rstd_r, nm_r = -mean_r * rstd_r) of row r reduced in the epilogue from the (sum, sumsq) partials of h
+  // (raff_rowstat: rows x raff_parts float2, the rowstat output of the GEMM that produced h); raff_ln_dim = channels of h.
+  const float* raff_rowstat;
+  int raff_parts;
+  const float* raff_c1;  // (B, N)
+  const float* raff_c2;  // (B, N)
+  float raff_eps;
+  int raff_ln_dim;
 };
 
 // value after bias -> final value; handles every epilogue except the memory side effects

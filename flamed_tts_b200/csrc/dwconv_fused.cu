@@ -303,10 +303,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) dwconv_ln_kernel(const __grid_con
         float a0, a1, b0, b1;
         unpack2(af.A2, a0, a1);
         unpack2(af.B2, b0, b1);
-        float* t = p.lnu_out + (int64_t)b * 3 * p.C + c;
+        float* t = p.lnu_out + (int64_t)b * p.lnu_vecs * p.C + c;
         *reinterpret_cast<float2*>(t) = g;
         *reinterpret_cast<float2*>(t + p.C) = make_float2(g.x * a0, g.y * a1);
         *reinterpret_cast<float2*>(t + 2 * p.C) = make_float2(g.x * (b3.x + b0), g.y * (b3.y + b1));
+        if (p.lnu_vecs == 4) {
+          const float2 sc = *reinterpret_cast<const float2*>(p.scale2 + (int64_t)b * p.mod_bstride + c);
+          float2 w2v = make_float2(1.f, 1.f);
+          if (p.ln2_w) w2v = *reinterpret_cast<const float2*>(p.ln2_w + c);
+          *reinterpret_cast<float2*>(t + 3 * p.C) = make_float2(w2v.x * (1.f + sc.x), w2v.y * (1.f + sc.y));
+        }
       }
     }
     {  // per-chunk (mean, M2) about the pivot: mean = pivot + S/n, M2 = Q - S^2/n
@@ -341,7 +347,7 @@ bool dwconv_fused_supported(const DwFused& p) {
   return p.C % CB == 0 && p.rowstat != nullptr && p.parts >= 2 && p.parts % 2 == 0 && p.tma_encode != nullptr &&
          (reinterpret_cast<uintptr_t>(p.h) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.g) & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(p.u) & 3) == 0 &&
-         (p.u != nullptr || (p.rowconst_out && p.lnu_out && p.gate && p.bias3 && p.scale));
+         (p.u != nullptr || (p.rowconst_out && p.lnu_out && p.gate && p.bias3 && p.scale && (p.lnu_vecs == 3 || (p.lnu_vecs == 4 && p.scale2))));
 }
 
 // LayerNorm-on-load + depthwise conv, persistent; writes u, the un-normalised d (into p.g) and the per-chunk partial

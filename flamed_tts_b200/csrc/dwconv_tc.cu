@@ -195,10 +195,11 @@ __global__ void __launch_bounds__(256) ln_consts_kernel(DwFused p, float2* __res
     ab[j] = make_float2(a, bb);
     if (lnu) {
       const float g = gate[(int64_t)b * p.mod_bstride + c];
-      float* t = lnu + (int64_t)b * 3 * p.C + c;
+      float* t = lnu + (int64_t)b * p.lnu_vecs * p.C + c;
       t[0] = g;
       t[p.C] = g * a;
       t[2 * p.C] = g * (bias3[c] + bb);
+      if (p.lnu_vecs == 4) t[3 * p.C] = (p.ln2_w ? p.ln2_w[c] : 1.f) * (1.f + p.scale2[(int64_t)b * p.mod_bstride + c]);
     }
   }
 }

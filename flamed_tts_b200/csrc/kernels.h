@@ -75,9 +75,14 @@ struct DwFused {
   // optional by-products for conv_3's epilogue (TapGemm::lnu_rowconst / lnu_table), all null or all set together with
   // u == nullptr: the inner residual u is then recomputed there instead of being written here
   float* rowconst_out;   // (B*L) float2 (rstd, -mean * rstd)
-  float* lnu_out;        // (B, 3, C): gate, gate * A, gate * (bias3 + B)
+  float* lnu_out;        // (B, lnu_vecs, C): gate, gate * A, gate * (bias3 + B) [, A2]
   const float* gate;     // adaLN gate of the block, sample stride mod_bstride
   const float* bias3;    // conv_3's bias (C)
+  // optional 4th vector A2 = ln2_w * (1 + scale2_b): column scale of the NEXT LayerNorm (the MLP branch's), which conv_3's
+  // epilogue applies to its second output (TapGemm::out2); lnu_vecs = 4 then, else 3
+  int lnu_vecs;
+  const float* ln2_w;    // (C), nullable (no affine)
+  const float* scale2;   // adaLN scale of the next LayerNorm, sample stride mod_bstride
 };
 void launch_dwconv_ln(const DwFused& p, float* part, int num_sms, cudaStream_t stream);
 bool dwconv_fused_supported(const DwFused& p);
@@ -132,6 +137,10 @@ void launch_noise_init(const float* noise, const float* cond, float temperature,
 void launch_philox_normal(const uint64_t* seed_dev, uint32_t tensor_id, float scale, const float* add, int64_t n,
                           float* out, cudaStream_t s);
 void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+// rows (r, c) of the two operand matrices of the algebraic LayerNorm (TapGemm::raff_*), bf16:
+//   s1[r, c] = w[c] * (1 + scale[r * stride + c]),  s2[r, c] = b[c] * (1 + scale[...]) + shift[r * stride + c]   (w, b nullable: 1, 0)
+void launch_ln_affine_rows(const float* w, const float* b, const float* shift, const float* scale, int64_t stride, int64_t rows,
+                           int C, bf16* s1, bf16* s2, cudaStream_t stream);
 void launch_fill_random(void* x, int is_bf16, int64_t n, uint32_t seed, float scale, cudaStream_t stream);
 
 // ---- cond down-sampler front end: xq[b,l,q*D+d] = prior[b,q,l,d] + qemb[q,d]; xm = xq * mask

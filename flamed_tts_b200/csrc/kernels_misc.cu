@@ -340,6 +340,25 @@ void launch_philox_normal(const uint64_t* seed_dev, uint32_t tensor_id, float sc
   philox_normal_kernel<<<nblk((n + 3) / 4), 256, 0, s>>>(seed_dev, tensor_id, scale, add, n, out);
   FLM_LAUNCH_CHECK();
 }
+namespace {
+__global__ void ln_affine_rows_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ shift,
+                                      const float* __restrict__ scale, int64_t stride, int64_t rows, int C,
+                                      bf16* __restrict__ s1, bf16* __restrict__ s2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int64_t r = i / C;
+  const int c = (int)(i - r * C);
+  const float m = 1.f + scale[r * stride + c];
+  s1[i] = __float2bfloat16_rn((w ? w[c] : 1.f) * m);
+  s2[i] = __float2bfloat16_rn(fmaf(b ? b[c] : 0.f, m, shift[r * stride + c]));
+}
+}  // namespace
+void launch_ln_affine_rows(const float* w, const float* b, const float* shift, const float* scale, int64_t stride, int64_t rows,
+                           int C, bf16* s1, bf16* s2, cudaStream_t stream) {
+  if (rows == 0) return;
+  ln_affine_rows_kernel<<<nblk(rows * C), 256, 0, stream>>>(w, b, shift, scale, stride, rows, C, s1, s2);
+  FLM_LAUNCH_CHECK();
+}
 void launch_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
   if (n == 0) return;
   f32_to_bf16_kernel<<<nblk(n), 256, 0, stream>>>(x, y, n);

@@ -305,11 +305,12 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const bool has_addend = kResid && EPI == EPI_GATE_RESID && p.addend != nullptr;
+  const bool has_out2 = kResid && EPI == EPI_GATE_RESID && p.out2 != nullptr;  // second output slab ring (lnu path)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + sch.stages * A_STAGE_BYTES;
   uint8_t* smem_r = smem_b + sch.stages * B_STAGE_BYTES;
   uint8_t* smem_d = smem_r + sch.nbuf * SLAB_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_d + (has_addend ? sch.nbuf * SLAB_BYTES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_d + ((has_addend || has_out2) ? sch.nbuf * SLAB_BYTES : 0));
   uint64_t* full_bar = bars;                       // [MAX_STAGES] operand stage filled (leader CTA's is the one used)
   uint64_t* empty_bar = bars + MAX_STAGES;         // [MAX_STAGES] operand stage consumed (multicast commit)
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;     // [2] accumulator stage complete (multicast commit)
@@ -331,7 +332,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     if (kResid) tma_prefetch_desc(&tmR);
-    if (has_addend) tma_prefetch_desc(&tmD);
+    if (has_addend || has_out2) tma_prefetch_desc(&tmD);
     for (int i = 0; i < sch.stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -434,10 +435,37 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int mt = 2 * mp + (int)rank;
       // sample of this thread's row (gate index); clamped for rows the TMA store will clip
       int bidx = 0;
-      if (EPI == EPI_GATE_RESID) {
+      if (EPI == EPI_GATE_RESID || (EPI == EPI_SILU && p.raff_c1 != nullptr)) {
         if (sch.flatten) bidx = (int)(((unsigned)mt * BLOCK_M + (unsigned)rrow) / (unsigned)p.T_out);
         else bidx = mt / sch.tiles_m_per_b;
         bidx = min(bidx, p.B - 1);
+      }
+      f32x2 raff_rs = 0ull, raff_nm = 0ull;  // (rstd, -mean * rstd) of this thread's row (row-affine SiLU epilogue)
+      if (EPI == EPI_SILU && p.raff_c1 != nullptr) {
+        int64_t grow;
+        bool ok;
+        if (sch.flatten) {
+          grow = (int64_t)mt * BLOCK_M + rrow;
+          ok = grow < (int64_t)p.B * p.T_out;
+        } else {
+          const int tb = mt / sch.tiles_m_per_b, tr = (mt % sch.tiles_m_per_b) * BLOCK_M + rrow;
+          grow = (int64_t)tb * p.T_out + tr;
+          ok = tb < p.B && tr < p.T_out;
+        }
+        if (ok) {
+          const float4* ps = reinterpret_cast<const float4*>(p.raff_rowstat) + (grow * p.raff_parts >> 1);
+          float sm = 0.f, sq = 0.f;
+          for (int k = 0; 2 * k < p.raff_parts; ++k) {
+            const float4 v4 = __ldg(ps + k);
+            sm += v4.x + v4.z;
+            sq += v4.y + v4.w;
+          }
+          const float inv_c = 1.0f / (float)p.raff_ln_dim;
+          const float mean = sm * inv_c;
+          const float rstd = rsqrtf(fmaxf(sq * inv_c - mean * mean, 0.f) + p.raff_eps);
+          raff_rs = pack2(rstd, rstd);
+          raff_nm = pack2(-mean * rstd, -mean * rstd);
+        }
       }
       mbar_wait_cluster(&tmem_full[as], aphase);
       tc_fence_after();
@@ -463,19 +491,20 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             nm2 = pack2(rc.y, rc.y);
           }
         }
-        const float* tab = p.lnu_table + (int64_t)bidx * 3 * p.N;
+        const float* tab = p.lnu_table + (int64_t)bidx * p.lnu_vecs * p.N;
 #pragma unroll 1
         for (int s = 0; s < SLABS; ++s) {
           uint8_t* rrow_ptr = smem_r + buf * SLAB_BYTES + rrow * 128;
 #pragma unroll 1
           for (int q = 0; q < 2; ++q) {
             const int n = nt * BLOCK_N + s * SLAB_COLS + half * 32 + q * 16;
-            float4 G[4], GA[4], GB[4];
+            float4 G[4], GA[4], GB[4], A2[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               G[j] = __ldg(reinterpret_cast<const float4*>(tab + n) + j);
               GA[j] = __ldg(reinterpret_cast<const float4*>(tab + p.N + n) + j);
               GB[j] = __ldg(reinterpret_cast<const float4*>(tab + 2 * p.N + n) + j);
+              if (has_out2) A2[j] = __ldg(reinterpret_cast<const float4*>(tab + 3 * p.N + n) + j);
             }
             float v[16];
             tmem_ld16(taddr + (uint32_t)(s * SLAB_COLS + half * 32 + q * 16), v);
@@ -485,7 +514,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               uint4* slot = reinterpret_cast<uint4*>(rrow_ptr + (((half * 4 + q * 2 + c) ^ (rrow & 7)) << 4));
               const uint4 hq = *slot;
               const uint32_t w[4] = {hq.x, hq.y, hq.z, hq.w};
-              uint32_t o[4];
+              uint32_t o[4], o2[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const f32x2 h2 = pack2(__uint_as_float(w[j] << 16), __uint_as_float(w[j] & 0xffff0000u));
@@ -503,8 +532,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 unpack2(r2, lo, hi);
                 __nv_bfloat162 tt = __floats2bfloat162_rn(lo, hi);
                 o[j] = *reinterpret_cast<uint32_t*>(&tt);
+                if (has_out2) {  // the column-scaled copy for the next LayerNorm's GEMM
+                  const float4 a = A2[c * 2 + (j >> 1)];
+                  unpack2(mul2(r2, (j & 1) ? pack2(a.z, a.w) : pack2(a.x, a.y)), lo, hi);
+                  tt = __floats2bfloat162_rn(lo, hi);
+                  o2[j] = *reinterpret_cast<uint32_t*>(&tt);
+                }
               }
               *slot = make_uint4(o[0], o[1], o[2], o[3]);
+              if (has_out2)
+                *reinterpret_cast<uint4*>(smem_d + buf * SLAB_BYTES + rrow * 128 + (((half * 4 + q * 2 + c) ^ (rrow & 7)) << 4)) =
+                    make_uint4(o2[0], o2[1], o2[2], o2[3]);
             }
           }
           fence_async_smem();
@@ -582,6 +620,17 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             *slot = make_uint4(o[0], o[1], o[2], o[3]);
           }
         } else {
+          if (EPI == EPI_SILU && p.raff_c1 != nullptr) {
+            // LayerNorm of the previous layer applied algebraically: value = rstd_r * acc + (nm_r * c1 + c2)
+            const float4* c1p = reinterpret_cast<const float4*>(p.raff_c1 + (int64_t)bidx * p.N + n);
+            const float4* c2p = reinterpret_cast<const float4*>(p.raff_c2 + (int64_t)bidx * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 c1 = __ldg(c1p + j), c2 = __ldg(c2p + j);
+              a2[2 * j] = fma2(a2[2 * j], raff_rs, fma2(pack2(c1.x, c1.y), raff_nm, pack2(c2.x, c2.y)));
+              a2[2 * j + 1] = fma2(a2[2 * j + 1], raff_rs, fma2(pack2(c1.z, c1.w), raff_nm, pack2(c2.z, c2.w)));
+            }
+          }
 #pragma unroll
           if (EPI == EPI_NONE && p.rowstat) {
 #pragma unroll
@@ -660,6 +709,7 @@ tapgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int s = 0; s < SLABS; ++s) {
           mbar_wait(&r_ready[buf], bphase);
           tma_store_3d(&tmO, smem_r + buf * SLAB_BYTES, nt * BLOCK_N + s * SLAB_COLS, tr.row, tr.b);
+          if (has_out2) tma_store_3d(&tmD, smem_d + buf * SLAB_BYTES, nt * BLOCK_N + s * SLAB_COLS, tr.row, tr.b);
           tma_store_commit();
           if (++buf == sch.nbuf) { buf = 0; bphase ^= 1; }
           if (++inflight > depth) {
@@ -696,7 +746,7 @@ constexpr int stage_bytes() { return A_STAGE_BYTES + (BLOCK_N / 2) * BLOCK_K * 2
 
 template <int BLOCK_N, int EPI>
 void launch_one(const TapGemm& p, const CUtensorMap* tm, Sched2 sch, int num_sms, cudaStream_t stream) {
-  const bool addend = EPI == EPI_GATE_RESID && p.addend != nullptr;
+  const bool addend = EPI == EPI_GATE_RESID && (p.addend != nullptr || p.out2 != nullptr);  // two slab rings
   const bool resid = epi_loads_residual(EPI);
   // slab buffers: enough loads in flight to cover HBM latency at the tensor-core rate; the rest goes to the ring
   sch.nbuf = addend ? 3 : (resid ? 4 : 3);
@@ -801,7 +851,9 @@ bool tapgemm_tc2_supported(const TapGemm& p) {
       return p.out_bf16 && p.out && p.resid_in && aligned(p.out, p.ldc) && aligned(p.resid_in, p.ldc);
     case EPI_GATE_RESID:
       return p.hres_bf16 && p.hres && aligned(p.hres, p.ld_res) &&
-             (!p.addend || (p.addend_bf16 && aligned(p.addend, p.ld_add)));
+             (!p.addend || (p.addend_bf16 && aligned(p.addend, p.ld_add))) &&
+             (!p.out2 || (p.lnu_table && p.lnu_vecs == 4 && !p.addend && aligned(p.out2, p.ld_out2))) &&
+             (!p.lnu_table || p.lnu_vecs == 3 || p.lnu_vecs == 4);
     default: return false;
   }
 }
@@ -862,6 +914,7 @@ void launch_tapgemm_tc2(const TapGemm& p, void* tma_encode, int num_sms, cudaStr
     encode_slab_map(encode, &tm[2], p.hres, p.ld_res, p.N, rows, nb, "hres");
     tm[3] = tm[2];
     if (p.addend) encode_slab_map(encode, &tm[4], p.addend, p.ld_add, p.N, rows, nb, "addend");
+    else if (p.out2) encode_slab_map(encode, &tm[4], p.out2, p.ld_out2, p.N, rows, nb, "out2");
     else tm[4] = tm[2];
   } else {
     encode_slab_map(encode, &tm[3], p.out, p.ldc, p.N, rows, nb, "out");

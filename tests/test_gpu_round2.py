@@ -434,17 +434,22 @@ print("WORST %%.4e" %% worst)
 """
 
 
-def test_tensor_core_depthwise_path_matches_the_oracle():
-    """FLAMED_B200_DWCONV=tc: the depthwise conv of the ConvNeXt blocks on the tensor cores (dwconv_tc.cu: Hankel operand
-    out of a channel time series, TMA-staged input, ldmatrix transposition, packed-bf16 LayerNorm) instead of the FMA
-    kernel.  Same bf16 tolerance as the production path (1e-2), at edge lengths (tiles that straddle samples, rows
-    shorter than the conv window) and at a bench-sized frame count.  The switch is read when a denoiser handle is
-    created, hence the subprocess."""
+@pytest.mark.parametrize("var,val", [("FLAMED_B200_DWCONV", "tc"), ("FLAMED_B200_MLPLN", "0")])
+def test_alternative_denoiser_paths_match_the_oracle(var, val):
+    """The two switches the denoiser reads when a handle is created (hence the subprocess), same bf16 tolerance as the
+    production path (1e-2), at edge lengths (tiles that straddle samples, rows shorter than the conv window) and at a
+    bench-sized frame count:
+      FLAMED_B200_DWCONV=tc  the depthwise conv of the ConvNeXt blocks on the tensor cores (dwconv_tc.cu: Hankel operand out
+                             of a channel time series, TMA-staged input, ldmatrix transposition, packed-bf16 LayerNorm)
+                             instead of the FMA kernel - an experiment, slower as measured (profiles/r2w);
+      FLAMED_B200_MLPLN=0    the MLP-branch LayerNorm as a pass of its own (ln_mod kernel) instead of the algebraic form
+                             inside conv_3's / mlp.0's epilogues (the default)."""
     import subprocess
     import sys
-    env = dict(os.environ, FLAMED_B200_DWCONV="tc")
+    env = dict(os.environ)
+    env[var] = val
     r = subprocess.run([sys.executable, "-c", _DWTC_SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     worst = float(r.stdout.strip().splitlines()[-1].split()[1])
-    print("tensor-core depthwise path: worst velocity rel-L2 %.3e" % worst)
+    print("%s=%s: worst velocity rel-L2 %.3e" % (var, val, worst))
     assert worst < 1e-2
