@@ -200,6 +200,7 @@ def run_step(model, dec, batches, args, device, from_host, collect_pcm=False):
                          temp_durgen=args.temp_durgen, temp_denoiser=args.temp_denoiser,
                          nsteps_durgen=args.nsteps_durgen, nsteps_denoiser=args.nsteps_denoiser, on_result=on_result,
                          rebucket=args.rebucket, row_budget=args.row_budget, max_batch=args.max_batch,
+                         batch_overhead_rows=args.batch_overhead_rows,
                          wav_to_host="pcm16" if from_host else None)
     for ev in st["ready"]:
         ev.synchronize()  # the PCM of every batch has landed in host memory
@@ -410,7 +411,8 @@ def workload_config(args, world, arm="ours"):
         c.update(precision=args.precision,
                  noise="device: Philox4x32-10 fused into the init kernels (seed from torch's generator)" if args.noise == "philox" else "device (torch cuda generator)",
                  batching=("re-bucketed by real frame count after the duration stage: <= %d samples and <= %d padded rows "
-                           "per back batch" % (args.max_batch, args.row_budget)) if args.rebucket else
+                           "per back batch, cuts minimising padded rows + %d rows per batch"
+                           % (args.max_batch, args.row_budget, args.batch_overhead_rows)) if args.rebucket else
                           "one sample_batch per front bucket (pipelined)",
                  l2="per-step working set (>5 GB activations per batch) exceeds the 126 MB L2; no flush needed",
                  parallelism="dp%d, one process per GPU, no collective in the loops, final NCCL gather of the PCM_16 "
@@ -431,6 +433,8 @@ def parse_args(argv=None):
     ap.add_argument("--utterances-long", type=int, default=64, help="config5: 30 s utterances per GPU")
     ap.add_argument("--front-batch", type=int, default=64, help="utterances per front (duration-stage) bucket")
     ap.add_argument("--max-batch", type=int, default=64, help="samples per back (denoiser / codec) batch")
+    ap.add_argument("--batch-overhead-rows", type=int, default=2500,
+                    help="cost of one more back batch in padded rows (parallel.bucket_by_rows)")
     ap.add_argument("--row-budget", type=int, default=32768, help="padded rows (B x L) per back batch")
     ap.add_argument("--no-rebucket", dest="rebucket", action="store_false")
     ap.add_argument("--nsteps-denoiser", type=int, default=128)
