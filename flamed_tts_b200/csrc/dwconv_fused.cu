@@ -24,7 +24,8 @@
 // front half) cost 0.517 ms per velocity evaluation against 0.414 + 0.106 ms for this kernel + the streaming apply (the
 // conv is bound by the FMA pipe and the issue slots, so every phase that keeps its warps away from FFMA2 shows); a
 // dedicated producer warp (160 threads) capped the registers at 168 and spilled; global loads of the row statistics
-// were sunk by the compiler next to their use (barrier stalls 0.64 per issue) until they were moved to cp.async.
+// were sunk by the compiler next to their use (barrier stalls 0.64 per issue) until they were moved to cp.async; three
+// resident blocks per SM (168 registers, 2-deep rings) were slower than two (0.409 vs 0.377 ms per velocity, profiles/r2z).
 //
 // 128 threads (thread = 2 channels x 32 frames); thread 0 issues one TMA tile copy per chunk two tiles ahead (62 frames
 // x 256 channels, out-of-range frames zero-filled), threads 0..61 prepare the per-row LayerNorm constants of the next
