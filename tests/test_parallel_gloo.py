@@ -47,6 +47,34 @@ def test_row_budget_bucketing():
     assert P.bucket_by_rows([], 100, 4) == [] and P.bucket_by_rows([5000], 100, 4) == [[0]]
 
 
+def test_row_budget_bucketing_is_optimal_for_its_cost():
+    """the cuts minimise sum(padded rows + overhead) over all contiguous partitions of the sorted lengths that respect the
+    two limits: checked against brute force on small pools, and the overhead knob moves the batch count monotonically"""
+    import itertools
+    rng = torch.Generator().manual_seed(3)
+    for trial in range(6):
+        n = 9 + trial
+        lens = torch.randint(5, 60, (n,), generator=rng).tolist()
+        budget, maxb, ovh = 150, 4, 17 + 10 * trial
+        srt = sorted(lens, reverse=True)
+
+        def cost(cuts):
+            c, a = 0, 0
+            for b in list(cuts) + [n]:
+                k = b - a
+                if k > maxb or (k > 1 and k * srt[a] > budget):
+                    return None
+                c += k * srt[a] + ovh
+                a = b
+            return c
+        best = min(c for r in range(n) for cuts in itertools.combinations(range(1, n), r) if (c := cost(cuts)) is not None)
+        got = P.bucket_by_rows(lens, budget, maxb, ovh)
+        assert sum(len(b) * max(lens[i] for i in b) + ovh for b in got) == best
+    lens = torch.randint(150, 1300, (300,), generator=rng).tolist()
+    counts = [len(P.bucket_by_rows(lens, 32768, 64, o)) for o in (0, 500, 2500, 10 ** 6)]
+    assert counts == sorted(counts, reverse=True) and counts[0] > counts[-1]
+
+
 def test_shard_of_a_global_pool_is_a_partition():
     """bench.py / synthesize.py: every rank derives its share from the same seeded pool with no communication"""
     for world in (2, 4, 8):
