@@ -200,7 +200,7 @@ def run_step(model, dec, batches, args, device, from_host, collect_pcm=False):
                          temp_durgen=args.temp_durgen, temp_denoiser=args.temp_denoiser,
                          nsteps_durgen=args.nsteps_durgen, nsteps_denoiser=args.nsteps_denoiser, on_result=on_result,
                          rebucket=args.rebucket, row_budget=args.row_budget, max_batch=args.max_batch,
-                         batch_overhead_rows=args.batch_overhead_rows,
+                         batch_overhead_rows=args.batch_overhead_rows, wave_rows=args.wave_rows,
                          wav_to_host="pcm16" if from_host else None)
     for ev in st["ready"]:
         ev.synchronize()  # the PCM of every batch has landed in host memory
@@ -433,6 +433,8 @@ def parse_args(argv=None):
     ap.add_argument("--utterances-long", type=int, default=64, help="config5: 30 s utterances per GPU")
     ap.add_argument("--front-batch", type=int, default=64, help="utterances per front (duration-stage) bucket")
     ap.add_argument("--max-batch", type=int, default=64, help="samples per back (denoiser / codec) batch")
+    ap.add_argument("--wave-rows", type=int, default=4736,
+                    help="rows of one GEMM wave (74 CTA pairs x 256 rows / 4 N tiles) in the batch cost model; 0 = ignore waves")
     ap.add_argument("--batch-overhead-rows", type=int, default=2500,
                     help="cost of one more back batch in padded rows (parallel.bucket_by_rows)")
     ap.add_argument("--row-budget", type=int, default=32768, help="padded rows (B x L) per back batch")

@@ -171,7 +171,7 @@ class Flamed(nn.Module):
 
     @torch.inference_mode()
     def sample_batches(self, batches, codec_decoder=None, temp_durgen=0.3, temp_denoiser=0.3, nsteps_durgen=64,
-                       nsteps_denoiser=64, on_result=None, rebucket=False, row_budget=32768, max_batch=64, batch_overhead_rows=2500,
+                       nsteps_denoiser=64, on_result=None, rebucket=False, row_budget=32768, max_batch=64, batch_overhead_rows=2500, wave_rows=4736,
                        wav_to_host=None):
         """Batched metadata entry point (the synthesize_via_metadata workload): `batches` is an iterable of dicts with
         phonemes (B,P), src_lens (B,), prompts (B,6,Lp), timbres (B,256) (host or device tensors).
@@ -241,7 +241,7 @@ class Flamed(nn.Module):
 
         if rebucket:
             self._sample_rebucketed(batches, main, finish, events, kw, temp_durgen, nsteps_durgen, row_budget, max_batch,
-                                    batch_overhead_rows)
+                                    batch_overhead_rows, wave_rows)
         else:
             side = self._side_stream
             side.wait_stream(main)  # inputs the caller prepared on its stream; later fronts must NOT wait for `main`
@@ -273,7 +273,7 @@ class Flamed(nn.Module):
         return None if on_result is not None else outs
 
     def _sample_rebucketed(self, batches, main, finish, events, kw, temp_durgen, nsteps_durgen, row_budget, max_batch,
-                           batch_overhead_rows=2500):
+                           batch_overhead_rows=2500, wave_rows=4736):
         from flamed_tts_b200.parallel import bucket_by_rows
         dev, pg = self.device, self.prior_generator
         pad_code = pg.config["codec"]["vocab_size"]
@@ -293,7 +293,7 @@ class Flamed(nn.Module):
         owner = [(fi, r) for fi, f in enumerate(fronts) for r in range(f[3].numel())]
         total = max(1, sum(lens))
         eng = pg.pva.engine()
-        for bi, idx in enumerate(bucket_by_rows(lens, row_budget, max_batch, batch_overhead_rows)):  # phase 2: pure enqueue
+        for bi, idx in enumerate(bucket_by_rows(lens, row_budget, max_batch, batch_overhead_rows, wave_rows)):  # phase 2: pure enqueue
             ev0, ev1 = events()
             ev0.record(main)
             src = [owner[j] for j in idx]

@@ -15,14 +15,25 @@ def bucket_by_length(lengths, max_batch=64):
     return [order[i:i + max_batch] for i in range(0, len(order), max_batch)]
 
 
-def bucket_by_rows(lengths, row_budget=32768, max_batch=64, batch_overhead_rows=2500):
+def batch_cost_rows(rows, wave_rows=4736, gemm_share=0.66):
+    """cost of a back batch of `rows` padded rows in row units: the GEMMs (gemm_share of a step) run 256-row x 256-column
+    tiles on 74 CTA pairs, i.e. in waves of 74 tiles = wave_rows rows of a 1024-column output, and a partly filled last
+    wave costs a full one; everything else is linear in the rows.  wave_rows = 0: plain padded rows."""
+    if not wave_rows:
+        return rows
+    tiles = -(-(-(-rows // 128)) // 2) * 4           # 128-row tiles paired, 4 N tiles each
+    waves = -(-tiles * 64 // wave_rows)              # one tile = 64 rows of the 1024-column output
+    return gemm_share * waves * wave_rows + (1.0 - gemm_share) * rows
+
+
+def bucket_by_rows(lengths, row_budget=32768, max_batch=64, batch_overhead_rows=2500, wave_rows=4736):
     """Sort by length (descending) and cut into contiguous buckets of <= max_batch samples and <= row_budget padded rows
-    (samples x longest member) so that  sum over buckets of (padded rows + batch_overhead_rows)  is minimal (dynamic
-    programme over the cut positions, O(n x max_batch)).  Short utterances travel in wide batches and long ones in narrow
-    batches - every launch sees about the same number of rows, what the GEMM tiles care about - while a bucket spans a
-    narrow range of lengths (little padding).  `batch_overhead_rows` is what one more batch costs in units of padded rows
-    (front-loaded tables, codec / conditioning launches, tile quantisation: ~24 ms against ~9.7 us per row on a B200,
-    profiles/r2y); 0 minimises the padding alone, a large value degenerates to the greedy widest-batches cut.
+    (samples x longest member) so that  sum over buckets of (batch_cost_rows(padded rows) + batch_overhead_rows)  is
+    minimal (dynamic programme over the cut positions, O(n x max_batch)).  Short utterances travel in wide batches and
+    long ones in narrow batches - every launch sees about the same number of rows, what the GEMM tiles care about - while
+    a bucket spans a narrow range of lengths (little padding), and batch sizes land just under a whole number of GEMM
+    waves.  `batch_overhead_rows` is what one more batch costs in units of padded rows (front-loaded tables, codec /
+    conditioning launches); 0 minimises the row cost alone, a large value degenerates to the greedy widest-batches cut.
     Returns lists of indices."""
     order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
     n = len(order)
@@ -38,7 +49,7 @@ def bucket_by_rows(lengths, row_budget=32768, max_batch=64, batch_overhead_rows=
         for k in range(1, max_batch + 1):
             if i + k > n or (k > 1 and k * longest > row_budget):
                 break
-            c = best[i] + k * longest + batch_overhead_rows
+            c = best[i] + batch_cost_rows(k * longest, wave_rows) + batch_overhead_rows
             if c < best[i + k]:
                 best[i + k] = c
                 prev[i + k] = i

@@ -68,11 +68,17 @@ def test_row_budget_bucketing_is_optimal_for_its_cost():
                 a = b
             return c
         best = min(c for r in range(n) for cuts in itertools.combinations(range(1, n), r) if (c := cost(cuts)) is not None)
-        got = P.bucket_by_rows(lens, budget, maxb, ovh)
+        got = P.bucket_by_rows(lens, budget, maxb, ovh, wave_rows=0)
         assert sum(len(b) * max(lens[i] for i in b) + ovh for b in got) == best
     lens = torch.randint(150, 1300, (300,), generator=rng).tolist()
     counts = [len(P.bucket_by_rows(lens, 32768, 64, o)) for o in (0, 500, 2500, 10 ** 6)]
     assert counts == sorted(counts, reverse=True) and counts[0] > counts[-1]
+    # the wave-aware cost: a partly filled last GEMM wave costs a full one; never below the linear cost's GEMM share
+    # (18 row pairs x 4 N tiles = 72 tiles fit one wave of 74, the 19th pair opens a second wave)
+    assert P.batch_cost_rows(18 * 256 + 1) > P.batch_cost_rows(18 * 256) + 0.6 * 4736 * 0.9
+    assert all(P.batch_cost_rows(r) >= r - 1e-6 for r in range(1, 40000, 97)) and P.batch_cost_rows(777, 0) == 777
+    wasted = lambda bs: sum(P.batch_cost_rows(len(b) * max(lens[i] for i in b)) for b in bs)
+    assert wasted(P.bucket_by_rows(lens, 32768, 64, 2500)) <= wasted(P.bucket_by_rows(lens, 32768, 64, 2500, wave_rows=0))
 
 
 def test_shard_of_a_global_pool_is_a_partition():
