@@ -23,18 +23,23 @@
 //     positions in front = the conv padding), so that a 992-position tile may straddle samples; rows that fall into the
 //     padding are computed and dropped.
 //
-// Per tile (32 channels x 992 owned positions), one CTA of 512 threads per SM:
-//   A. the tile's h rows arrive by TMA (32 boxes of 32 positions x 32 channels, SWIZZLE_64B, issued one tile ahead;
-//      positions outside a sample are out of bounds for the tensor map = zeros).  ldmatrix.x4.trans reads 8 positions x
-//      32 channels per warp instruction and hands every thread (channel, two consecutive positions) pairs - the
-//      transposition is free; the LayerNorm constants of the positions (launch_dwconv_tc's first kernel reduced the GEMM
-//      epilogue's row partials to (rstd, -mean rstd) per row) and the per-sample affine are applied in registers and the
-//      bf16 pairs go to the channel series X (4-byte stores, conflict free because the series pitch is an odd multiple of
-//      16 B);  u itself (the inner residual conv_3's epilogue adds) is written row-major by a second pass;
-//   B. one thread issues 32 channels x 3 MMAs into the 512 TMEM columns (16 per channel);
-//   C. the epilogue reads TMEM thread-per-row (8 positions x 8 channels per thread), adds the bias, stores d, and
-//      reduces (sum, sum of squares about the per-channel pivot) over the warp's rows with a shuffle butterfly:
-//      one (mean, M2) partial per (sample, 256-position chunk, channel), merged in a fixed order by the last kernel.
+// STATUS: opt-in experiment (FLAMED_B200_DWCONV=tc), parity-tested, 18-27 % SLOWER than the FMA kernel as measured
+// (profiles/r2w/SUMMARY.md): the MMAs are free (tensor pipe 3-4 % busy) but conversion, statistics and addressing still
+// cost ~28 thread instructions per output at ~31 % issue-slot utilisation; the floor of the formulation is ~8.
+//
+// Per tile (32 channels x 992 owned positions), one CTA per SM = four independent pipelines of 4 warps + 4 issue warps.
+// Warp group j owns the 8-channel chunk j of the tile end to end:
+//   A. the tile's h rows arrive by TMA (32 boxes of 32 positions x 32 channels, SWIZZLE_64B, issued one tile ahead after
+//      an L2 prefetch; positions outside a sample are out of bounds for the tensor map = zeros).  ldmatrix.x4.trans reads
+//      32 positions x 8 channels per warp instruction and hands every thread (channel, two consecutive positions) pairs -
+//      the transposition is free.  LayerNorm + modulate are TWO packed-bf16 FMAs per pair, (x rstd + nm) A + B, with the
+//      row constants (launch_dwconv_tc's first kernel reduces the GEMM epilogue's row partials) held as bf16 pairs in
+//      shared memory; the pairs go to the channel series X (4-byte stores, conflict free because the series pitch is an
+//      odd multiple of 16 B).  u itself is NOT written: conv_3's epilogue recomputes the inner residual (TapGemm::lnu_*);
+//   B. the group's issue warp issues 8 channels x 3 MMAs into the group's 128 TMEM columns (16 per channel);
+//   C. the group reads TMEM thread-per-row (8 positions x 8 channels per thread), adds the bias, stores d, and reduces
+//      (sum, sum of squares about the per-channel pivot) over the warp's rows with a shuffle butterfly: one (mean, M2)
+//      partial per (sample, 256-position chunk, channel), merged in a fixed order by the last kernel.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -684,7 +689,7 @@ size_t dwconv_tc_part_bytes(int B, int L, int C) {
   return (size_t)B * g.kmax * C * sizeof(float2);
 }
 
-// LayerNorm-on-load + depthwise conv on the tensor cores + GroupNorm statistics: writes u (if non-null), the
+// LayerNorm-on-load + depthwise conv on the tensor cores + GroupNorm statistics (p.u must be null: see lnu below): writes the
 // un-normalised d (into p.g) and the GroupNorm scale / offset (B, C).  Follow with an in-place launch_gn_stream on p.g.
 // Scratch: rowconst (B*L float2), ab (B*C float2), part (dwconv_tc_part_bytes).
 // gate / bias3 / lnu (all nullable together): adaLN gate of the block (per sample, stride p.mod_bstride), conv_3's bias and the
