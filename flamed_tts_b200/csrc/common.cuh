@@ -128,10 +128,6 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("FLAMED_B200_PDL"); return !(e && e[0] == '0'); }();
-  return on;
-}
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -141,7 +137,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = 1;
   FLM_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One velocity evaluation of the bf16 denoiser (LayerNorm-fused depthwise conv, programmatic dependent launches)
 against the CPU oracle at edge and bench sizes, reproducibility, and timing per kernel class at bench-sized batches.
-usage: python tools/fused_check.py          (FLAMED_B200_PDL=0 disables the dependent launches for an A/B run)"""
+usage: python tools/fused_check.py"""
 import os
 import sys
 import time

@@ -35,6 +35,9 @@ cases = [  # mode, B, T, K, N, ntaps, dil, epi, out_bf16
     (1, 64, 550, 1024, 1024, 1, 1, 5 | 0x300, 0),     # 18: same, short bucket
     (1, 64, 110000, 64, 64, 1, 1, 4, 1),              # 19: codec ResidualUnit k1 conv + skip, C=64
     (1, 64, 55000, 128, 128, 1, 1, 4, 1),             # 20: C=128
+    (1, 1, 76800, 256, 1024, 1, 1, 0, 1),             # 21: proj_in shape (K=256), bf16 out: CTA-pair kernel
+    (1, 1, 32768, 256, 1024, 1, 1, 0, 1),             # 22: the same at a bench-sized batch
+    (1, 1, 32768, 1024, 1024, 1, 1, 0, 1),            # 23: plain K=1024 at a bench-sized batch
 ]
 if len(sys.argv) > 1:
     cases = [cases[int(a)] for a in sys.argv[1:]]
