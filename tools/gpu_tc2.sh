@@ -5,5 +5,4 @@ timeout 120 python tools/tc2_check.py ${CASES} > gpurun_out/${TAG}_check.txt 2>&
 cat gpurun_out/${TAG}_check.txt | tail -40
 if [ -n "$BENCH" ]; then
   REPS=20 timeout 200 python tools/gemm_bench.py > gpurun_out/${TAG}_gemm.txt 2>&1; echo "gemm=$?"; cat gpurun_out/${TAG}_gemm.txt
-  FLAMED_B200_GEMM=1 REPS=20 timeout 200 python tools/gemm_bench.py 14 15 16 17 18 19 20 > gpurun_out/${TAG}_gemm_gen1.txt 2>&1; cat gpurun_out/${TAG}_gemm_gen1.txt
 fi
