@@ -750,7 +750,8 @@ void launch_one(const TapGemm& p, const CUtensorMap* tm, Sched2 sch, int num_sms
   const bool resid = epi_loads_residual(EPI);
   // slab buffers: enough loads in flight to cover HBM latency at the tensor-core rate; the rest goes to the ring
   sch.nbuf = addend ? 3 : (resid ? 4 : 3);
-  // (two rings: 3 slab pairs measured best - 2 pairs 0.175 ms, 3 pairs 0.149 ms, 4 pairs 0.163 ms at M = 76 800, profiles/r2z)
+  // (two rings: 3 slab pairs measured best - 2 pairs 0.175 ms, 3 pairs 0.149 ms, 4 pairs 0.163 ms at M = 76 800; 4 residual +
+  //  2 second-output buffers with separate hand-offs: GEMM class 1.455 vs 1.423 ms per velocity, profiles/r2z)
   sch.store_depth = 1;  // (measured: 0, 1 and 2 are within noise of each other, profiles/r2w)
   const int epi_bytes = sch.nbuf * SLAB_BYTES * (addend ? 2 : 1);
   int stages = (SMEM_LIMIT - 1024 - BAR_BYTES - epi_bytes) / stage_bytes<BLOCK_N>();
