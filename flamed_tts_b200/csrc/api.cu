@@ -613,9 +613,12 @@ struct flm_denoiser : Engine {
   }
   bool xb_fresh = false;  // xb holds bf16(x) of the current state
   int launches_per_step() const {  // steady state (the first step of a loop adds the f32 -> bf16 conversion of x0)
-    // bf16: proj_in + per block (LN-fused depthwise conv, statistics merge, GroupNorm apply, 2 GEMMs, LN, 2 GEMMs)
-    if (fused()) return 1 + (int)blocks.size() * 8 + 7;
-    return 1 + (int)blocks.size() * 8 + 7;  // fp32: proj_in + per block (LN, dwconv, GN apply, 2 GEMMs, LN, 2 GEMMs)
+    const int nb = (int)blocks.size();
+    // bf16: proj_in + per block (LayerNorm-fused depthwise conv [tensor-core form: + 2 helper kernels], statistics merge,
+    // GroupNorm apply, conv_2, conv_3, [LayerNorm unless applied algebraically], mlp.0, mlp.2) + the FinalLayer's
+    // (depthwise, merge, GroupNorm apply, conv_2, conv_3, LayerNorm, conv_out)
+    if (fused()) return 1 + nb * (mlp_ln_fused ? 7 : 8) + 7 + (dw_tensor ? nb + 1 : 0);
+    return 1 + nb * 8 + 7;  // fp32: proj_in + per block (LN, dwconv, GN apply, 2 GEMMs, LN, 2 GEMMs) + the FinalLayer's 7
   }
 
   bool ensure(int B, int L, int nfe) {
